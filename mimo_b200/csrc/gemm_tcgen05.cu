@@ -1,0 +1,513 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[M,N] = epilogue( A[M,K] . W[N,K]^T )          fp16/bf16 operands, fp32 accumulate in TMEM
+//
+// One CTA per SM loops over 128 x BN output tiles (static round-robin schedule, n-tile fastest so that CTAs
+// running concurrently share A tiles in L2). Roles (256 threads):
+//   warp 0 lane 0 : TMA producer  - fills a ring of {A 128x64, W BNx64} 128B-swizzled stages
+//   warp 1 lane 0 : MMA issuer    - tcgen05.mma.cta_group::1.kind::f16 128xBNx16, accumulators double-buffered
+//                                   in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue      - tcgen05.ld 32 lanes x 32 columns, fused bias / per-frame vector / residual /
+//                                   scale / SiLU / GEGLU, 16-byte vector stores
+// Convolution mode replaces the A loads by 4-D TMA boxes {64 ch, TW, TH, TN} over the NHWC input, one box per
+// (tap, 64-channel block, source tensor); TMA's out-of-bounds zero fill is the conv's zero padding and also
+// the K tail. Two source tensors give the up-blocks' channel concat without materialising it.
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include "../../include/mimo_b200.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace mimo {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 x 16-bit = one 128-byte swizzle row
+constexpr int kGemmThreads = 256;
+
+struct EpiArgs {
+  const void* bias;
+  const void* rowvec;
+  const void* residual;
+  void* out;
+  long long rows_per_group;
+  long long ld_res;
+  long long ldo;
+  float scale;
+  int act;
+};
+
+struct ConvGeom {
+  int conv;  // 0: plain GEMM rows; 1: rows are (n, y, x) footprints
+  int H, W, NI;
+  int TW, TH, TN;
+  int tiles_w, tiles_h;
+  int ctot;       // c0 + c1
+  int c0;         // channels of source 0
+  int kb0, kb1;   // 64-channel blocks per tap for source 0 / 1
+  int a_bytes;    // bytes one A box deposits in shared memory
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 160 ? 5 : (BN >= 128 ? 6 : 8));
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool kBf16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB, int M, int N, int num_m_tiles, int num_n_tiles,
+                    int num_k_blocks, ConvGeom g, EpiArgs ep) {
+  using Cfg = GemmCfg<BN>;
+  using C = Cvt<kBf16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    uint32_t it = 0;
+    const int kb_per_tap = g.kb0 + g.kb1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / num_n_tiles;
+      const int n_tile = tile % num_n_tiles;
+      int x0 = 0, y0 = 0, n0 = 0;
+      if (g.conv) {
+        x0 = (m_tile % g.tiles_w) * g.TW;
+        y0 = ((m_tile / g.tiles_w) % g.tiles_h) * g.TH;
+        n0 = (m_tile / (g.tiles_w * g.tiles_h)) * g.TN;
+      }
+      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+        const uint32_t stage = it % Cfg::kStages;
+        const uint32_t phase = (it / Cfg::kStages) & 1u;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + BM * BK * 2;
+        if (!g.conv) {
+          mbar_expect_tx(&full_bar[stage], BM * BK * 2 + BN * BK * 2);
+          tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, m_tile * BM);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
+        } else {
+          const int tap = kb / kb_per_tap;
+          const int rem = kb - tap * kb_per_tap;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          mbar_expect_tx(&full_bar[stage], g.a_bytes + BN * BK * 2);
+          int kcoord;
+          if (rem < g.kb0) {
+            tma_load_4d(sa, &tmA0, &full_bar[stage], rem * BK, x0 + dx, y0 + dy, n0);
+            kcoord = tap * g.ctot + rem * BK;
+          } else {
+            tma_load_4d(sa, &tmA1, &full_bar[stage], (rem - g.kb0) * BK, x0 + dx, y0 + dy, n0);
+            kcoord = tap * g.ctot + g.c0 + (rem - g.kb0) * BK;
+          }
+          tma_load_2d(sb, &tmB, &full_bar[stage], kcoord, n_tile * BN);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN, kBf16, false, false);
+    uint32_t it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t acc = lt & 1u;
+      const uint32_t acc_phase = (lt >> 1) & 1u;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+        const uint32_t stage = it % Cfg::kStages;
+        const uint32_t phase = (it / Cfg::kStages) & 1u;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + BM * BK * 2;
+        const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+        const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
+          umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+      }
+      tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = ew * 32 + lane;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int m_tile = tile / num_n_tiles;
+      const int n_tile = tile % num_n_tiles;
+      const uint32_t acc = lt & 1u;
+      const uint32_t acc_phase = (lt >> 1) & 1u;
+
+      long long row;
+      bool row_ok;
+      if (!g.conv) {
+        row = static_cast<long long>(m_tile) * BM + r;
+        row_ok = row < M;
+      } else {
+        const int x0 = (m_tile % g.tiles_w) * g.TW;
+        const int y0 = ((m_tile / g.tiles_w) % g.tiles_h) * g.TH;
+        const int n0 = (m_tile / (g.tiles_w * g.tiles_h)) * g.TN;
+        const int x = r % g.TW, y = (r / g.TW) % g.TH, n = r / (g.TW * g.TH);
+        row_ok = (n < g.TN) && (x0 + x < g.W) && (y0 + y < g.H) && (n0 + n < g.NI);
+        row = (static_cast<long long>(n0 + n) * g.H + (y0 + y)) * g.W + (x0 + x);
+      }
+      const long long grp = ep.rowvec ? row / ep.rows_per_group : 0;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+
+      if (ep.act != MIMO_ACT_GEGLU) {
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = n_tile * BN + c * 32;
+          if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int col = col0 + q * 8;
+              if (col < N) {  // N % 8 == 0
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+                if (ep.bias) {
+                  const uint4 b = __ldg(reinterpret_cast<const uint4*>(
+                      static_cast<const typename C::T*>(ep.bias) + col));
+                  const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 t = C::unpack(bw[j]);
+                    f[2 * j] += t.x;
+                    f[2 * j + 1] += t.y;
+                  }
+                }
+                if (ep.rowvec) {
+                  const uint4 b = __ldg(reinterpret_cast<const uint4*>(
+                      static_cast<const typename C::T*>(ep.rowvec) + grp * N + col));
+                  const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 t = C::unpack(bw[j]);
+                    f[2 * j] += t.x;
+                    f[2 * j + 1] += t.y;
+                  }
+                }
+                if (ep.residual) {
+                  const uint4 b = *reinterpret_cast<const uint4*>(
+                      static_cast<const typename C::T*>(ep.residual) + row * ep.ld_res + col);
+                  const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 t = C::unpack(bw[j]);
+                    f[2 * j] += t.x;
+                    f[2 * j + 1] += t.y;
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  f[j] *= ep.scale;
+                  if (ep.act == MIMO_ACT_SILU) f[j] = silu_f(f[j]);
+                }
+                uint4 o;
+                o.x = C::pack(f[0], f[1]);
+                o.y = C::pack(f[2], f[3]);
+                o.z = C::pack(f[4], f[5]);
+                o.w = C::pack(f[6], f[7]);
+                *reinterpret_cast<uint4*>(static_cast<typename C::T*>(ep.out) + row * ep.ldo + col) = o;
+              }
+            }
+          }
+        }
+      } else {
+        // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates.
+        constexpr int HALF = BN / 2;
+        for (int c = 0; c < HALF / 32; ++c) {
+          uint32_t v[32], gt[32];
+          tmem_ld_x32(taddr + c * 32, v);
+          tmem_ld_x32(taddr + HALF + c * 32, gt);
+          tmem_ld_wait();
+          const int pcol0 = n_tile * BN + c * 32;          // packed column of the value half
+          const int ocol0 = n_tile * HALF + c * 32;        // output column
+          if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float fv[8], fg[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                fv[j] = __uint_as_float(v[q * 8 + j]);
+                fg[j] = __uint_as_float(gt[q * 8 + j]);
+              }
+              if (ep.bias) {
+                const typename C::T* bp = static_cast<const typename C::T*>(ep.bias);
+                const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(bp + pcol0 + q * 8));
+                const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(bp + pcol0 + HALF + q * 8));
+                const uint32_t w0[4] = {b0.x, b0.y, b0.z, b0.w};
+                const uint32_t w1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 t0 = C::unpack(w0[j]);
+                  const float2 t1 = C::unpack(w1[j]);
+                  fv[2 * j] += t0.x;
+                  fv[2 * j + 1] += t0.y;
+                  fg[2 * j] += t1.x;
+                  fg[2 * j + 1] += t1.y;
+                }
+              }
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fv[j] * gelu_erf_f(fg[j]);
+              uint4 o;
+              o.x = C::pack(f[0], f[1]);
+              o.y = C::pack(f[2], f[3]);
+              o.z = C::pack(f[4], f[5]);
+              o.w = C::pack(f[6], f[7]);
+              *reinterpret_cast<uint4*>(static_cast<typename C::T*>(ep.out) + row * ep.ldo + ocol0 + q * 8) = o;
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator buffer are complete (wait::ld above): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool kBf16>
+static int launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, int M, int N, int mt,
+                      int nt, int nkb, const ConvGeom& g, const EpiArgs& ep, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, kBf16>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(gemm)", e);
+    attr_done = true;
+  }
+  const int tiles = mt * nt;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a0, a1, b, M, N, mt, nt, nkb, g, ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("gemm launch", e);
+  return MIMO_OK;
+}
+
+template <bool kBf16>
+static int launch_bn(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, int M, int N,
+                     int mt, int nt, int nkb, const ConvGeom& g, const EpiArgs& ep, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch_cfg<64, kBf16>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+    case 128: return launch_cfg<128, kBf16>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+    case 160: return launch_cfg<160, kBf16>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+    case 256: return launch_cfg<256, kBf16>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+  }
+  return set_error(MIMO_ERR_ARG, "gemm: unsupported BN");
+}
+
+static int g_force_bn = 0;  // test hook (mimo_debug_force_bn)
+
+// Tile-width choice: least padded columns first, then the widest tile (fewer A re-reads, higher MMA N).
+int pick_bn(int N, bool geglu, long long m_tiles) {
+  if (g_force_bn) return g_force_bn;
+  if (geglu) {
+    if (N % 256 == 0) return 256;
+    if (N % 128 == 0) return 128;
+    return 64;
+  }
+  const int cands[4] = {256, 160, 128, 64};
+  int best = 64;
+  double best_eff = -1.0;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const int nt = (N + bn - 1) / bn;
+    double eff = static_cast<double>(N) / (static_cast<double>(nt) * bn);
+    // small problems: prefer enough tiles to occupy the machine
+    const long long tiles = m_tiles * nt;
+    if (tiles < num_sms() && bn > 64) eff *= 0.5 + 0.5 * static_cast<double>(tiles) / num_sms();
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+static EpiArgs make_epi(const mimo_epilogue& e, void* out, long long ldo) {
+  EpiArgs a;
+  a.bias = e.bias;
+  a.rowvec = e.rowvec;
+  a.residual = e.residual;
+  a.out = out;
+  a.rows_per_group = e.rows_per_group > 0 ? e.rows_per_group : 1;
+  a.ld_res = e.ld_res;
+  a.ldo = ldo;
+  a.scale = e.scale;
+  a.act = e.act;
+  return a;
+}
+
+}  // namespace mimo
+
+using namespace mimo;
+
+extern "C" int mimo_debug_force_bn(int bn) {
+  g_force_bn = bn;
+  return 0;
+}
+
+extern "C" int mimo_gemm_geglu_granule(int32_t N) { return pick_bn(N, true, 1 << 20) / 2; }
+
+extern "C" int mimo_gemm(const mimo_gemm_params* p, void* stream) {
+  if (!p || !p->a || !p->w || !p->out) return set_error(MIMO_ERR_ARG, "mimo_gemm: null pointer");
+  if (p->M <= 0 || p->N <= 0 || p->K <= 0) return set_error(MIMO_ERR_ARG, "mimo_gemm: empty problem");
+  if ((p->K % 8) || (p->lda % 8) || (p->ldw % 8) || (p->N % 8) || (p->ldo % 8))
+    return set_error(MIMO_ERR_ARG, "mimo_gemm: K, N, lda, ldw, ldo must be multiples of 8");
+  if (p->ep.residual && (p->ep.ld_res % 8)) return set_error(MIMO_ERR_ARG, "mimo_gemm: ld_res % 8 != 0");
+  const bool geglu = p->ep.act == MIMO_ACT_GEGLU;
+  if (int rc = ensure_device()) return rc;
+  const int mt = (p->M + BM - 1) / BM;
+  const int bn = pick_bn(p->N, geglu, mt);
+  if (geglu && (p->N % bn)) return set_error(MIMO_ERR_ARG, "mimo_gemm: GEGLU needs N % tile == 0");
+  const int nt = (p->N + bn - 1) / bn;
+  const int nkb = (p->K + BK - 1) / BK;
+
+  CUtensorMap ta, tb;
+  const uint64_t adim[2] = {static_cast<uint64_t>(p->K), static_cast<uint64_t>(p->M)};
+  const uint64_t astr[1] = {static_cast<uint64_t>(p->lda) * 2};
+  const uint32_t abox[2] = {BK, BM};
+  if (int rc = encode_tmap(&ta, p->dtype, 2, p->a, adim, astr, abox)) return rc;
+  const uint64_t bdim[2] = {static_cast<uint64_t>(p->K), static_cast<uint64_t>(p->N)};
+  const uint64_t bstr[1] = {static_cast<uint64_t>(p->ldw) * 2};
+  const uint32_t bbox[2] = {BK, static_cast<uint32_t>(bn)};
+  if (int rc = encode_tmap(&tb, p->dtype, 2, p->w, bdim, bstr, bbox)) return rc;
+
+  ConvGeom g = {};
+  EpiArgs ep = make_epi(p->ep, p->out, p->ldo);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dtype == MIMO_BF16) return launch_bn<true>(bn, ta, ta, tb, p->M, p->N, mt, nt, nkb, g, ep, st);
+  return launch_bn<false>(bn, ta, ta, tb, p->M, p->N, mt, nt, nkb, g, ep, st);
+}
+
+extern "C" int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream) {
+  if (!p || !p->x0 || !p->w || !p->out) return set_error(MIMO_ERR_ARG, "mimo_conv3x3: null pointer");
+  if (p->n <= 0 || p->h <= 0 || p->w_ <= 0 || p->cout <= 0 || p->c0 <= 0)
+    return set_error(MIMO_ERR_ARG, "mimo_conv3x3: empty problem");
+  const int c1 = p->x1 ? p->c1 : 0;
+  if ((p->c0 % 8) || (c1 % 8) || (p->cout % 8) || (p->ldo % 8))
+    return set_error(MIMO_ERR_ARG, "mimo_conv3x3: channel counts must be multiples of 8");
+  if (p->ep.act == MIMO_ACT_GEGLU) return set_error(MIMO_ERR_ARG, "mimo_conv3x3: GEGLU not supported");
+  if (int rc = ensure_device()) return rc;
+
+  ConvGeom g = {};
+  g.conv = 1;
+  g.H = p->h;
+  g.W = p->w_;
+  g.NI = p->n;
+  g.TW = p->w_ < BM ? p->w_ : BM;
+  g.TH = BM / g.TW;
+  if (g.TH > p->h) g.TH = p->h;
+  if (g.TH < 1) g.TH = 1;
+  g.TN = BM / (g.TW * g.TH);
+  if (g.TN > p->n) g.TN = p->n;
+  if (g.TN < 1) g.TN = 1;
+  if (g.TN > 1 && g.TH != p->h) g.TN = 1;  // several images per tile only when a tile spans whole images
+  g.tiles_w = (p->w_ + g.TW - 1) / g.TW;
+  g.tiles_h = (p->h + g.TH - 1) / g.TH;
+  const int tiles_n = (p->n + g.TN - 1) / g.TN;
+  g.ctot = p->c0 + c1;
+  g.c0 = p->c0;
+  g.kb0 = (p->c0 + BK - 1) / BK;
+  g.kb1 = (c1 + BK - 1) / BK;
+  g.a_bytes = g.TW * g.TH * g.TN * BK * 2;
+  const int mt = g.tiles_w * g.tiles_h * tiles_n;
+  const int bn = pick_bn(p->cout, false, mt);
+  const int nt = (p->cout + bn - 1) / bn;
+  const int nkb = 9 * (g.kb0 + g.kb1);
+  const long long Mrows = static_cast<long long>(p->n) * p->h * p->w_;
+  if (Mrows > 0x7fffffffLL) return set_error(MIMO_ERR_ARG, "mimo_conv3x3: too many pixels");
+
+  CUtensorMap ta0, ta1, tb;
+  {
+    const uint64_t dim[4] = {static_cast<uint64_t>(p->c0), static_cast<uint64_t>(p->w_),
+                             static_cast<uint64_t>(p->h), static_cast<uint64_t>(p->n)};
+    const uint64_t str[3] = {static_cast<uint64_t>(p->c0) * 2, static_cast<uint64_t>(p->w_) * p->c0 * 2,
+                             static_cast<uint64_t>(p->h) * p->w_ * p->c0 * 2};
+    const uint32_t box[4] = {BK, static_cast<uint32_t>(g.TW), static_cast<uint32_t>(g.TH),
+                             static_cast<uint32_t>(g.TN)};
+    if (int rc = encode_tmap(&ta0, p->dtype, 4, p->x0, dim, str, box)) return rc;
+  }
+  if (c1) {
+    const uint64_t dim[4] = {static_cast<uint64_t>(c1), static_cast<uint64_t>(p->w_),
+                             static_cast<uint64_t>(p->h), static_cast<uint64_t>(p->n)};
+    const uint64_t str[3] = {static_cast<uint64_t>(c1) * 2, static_cast<uint64_t>(p->w_) * c1 * 2,
+                             static_cast<uint64_t>(p->h) * p->w_ * c1 * 2};
+    const uint32_t box[4] = {BK, static_cast<uint32_t>(g.TW), static_cast<uint32_t>(g.TH),
+                             static_cast<uint32_t>(g.TN)};
+    if (int rc = encode_tmap(&ta1, p->dtype, 4, p->x1, dim, str, box)) return rc;
+  } else {
+    ta1 = ta0;
+  }
+  {
+    const uint64_t dim[2] = {static_cast<uint64_t>(9) * g.ctot, static_cast<uint64_t>(p->cout)};
+    const uint64_t str[1] = {static_cast<uint64_t>(9) * g.ctot * 2};
+    const uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+    if (int rc = encode_tmap(&tb, p->dtype, 2, p->w, dim, str, box)) return rc;
+  }
+  EpiArgs ep = make_epi(p->ep, p->out, p->ldo);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dtype == MIMO_BF16)
+    return launch_bn<true>(bn, ta0, ta1, tb, static_cast<int>(Mrows), p->cout, mt, nt, nkb, g, ep, st);
+  return launch_bn<false>(bn, ta0, ta1, tb, static_cast<int>(Mrows), p->cout, mt, nt, nkb, g, ep, st);
+}

@@ -1,0 +1,276 @@
+"""Tensor-level wrappers over the C ABI. PyTorch is only the owner of device memory and of the stream here:
+every function enqueues exactly the kernels of one C entry point on torch's current CUDA stream.
+
+Activations are channels-last 2-D views: [rows, C] with rows = (frame-sample, y, x).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+
+_launches = 0  # number of C-ABI compute calls issued (bench.py's gpu_launches evidence)
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(k: int = 1) -> None:
+    global _launches
+    _launches += k
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return L.F16
+    if t.dtype == torch.bfloat16:
+        return L.BF16
+    raise L.MimoError(f"unsupported dtype {t.dtype}: engine tensors are fp16 or bf16")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise L.MimoError("mimo_b200 ops need CUDA tensors (there is no CPU fallback)")
+    return t.data_ptr()
+
+
+def _epilogue(bias=None, rowvec=None, rows_per_group=1, residual=None, scale=1.0, act=L.ACT_NONE) -> L.Epilogue:
+    ep = L.Epilogue()
+    ep.bias = _ptr(bias)
+    ep.rowvec = _ptr(rowvec)
+    ep.rows_per_group = int(rows_per_group)
+    ep.residual = _ptr(residual)
+    ep.ld_res = residual.stride(0) if residual is not None else 0
+    ep.scale = float(scale)
+    ep.act = int(act)
+    return ep
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, rowvec=None,
+         rows_per_group=1, residual=None, scale=1.0, act=L.ACT_NONE) -> torch.Tensor:
+    """out[M, N(or N/2 for GEGLU)] = epilogue(a[M, K] @ w[N, K]^T)."""
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if act == L.ACT_GEGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=a.dtype, device=a.device)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    p = L.GemmParams()
+    p.a, p.lda = _ptr(a), a.stride(0)
+    p.w, p.ldw = _ptr(w), w.stride(0)
+    p.out, p.ldo = _ptr(out), out.stride(0)
+    p.M, p.N, p.K = M, N, K
+    p.dtype = _dt(a)
+    p.ep = _epilogue(bias, rowvec, rows_per_group, residual, scale, act)
+    L.check(L.load().mimo_gemm(C.byref(p), _stream()), "mimo_gemm")
+    _count()
+    return out
+
+
+def conv3x3(x0: torch.Tensor, w: torch.Tensor, n: int, h: int, wd: int, out: Optional[torch.Tensor] = None, *,
+            x1: Optional[torch.Tensor] = None, bias=None, rowvec=None, residual=None, scale=1.0,
+            act=L.ACT_NONE) -> torch.Tensor:
+    """3x3/s1/p1 conv over channels-last x0 [n*h*wd, c0] (+ x1 [n*h*wd, c1]); w packed [cout, 9*(c0+c1)]."""
+    c0 = x0.shape[1]
+    c1 = x1.shape[1] if x1 is not None else 0
+    cout = w.shape[0]
+    assert x0.is_contiguous() and (x1 is None or x1.is_contiguous()) and w.is_contiguous()
+    assert w.shape[1] == 9 * (c0 + c1) and x0.shape[0] == n * h * wd
+    if out is None:
+        out = torch.empty((n * h * wd, cout), dtype=x0.dtype, device=x0.device)
+    p = L.Conv3x3Params()
+    p.x0, p.c0 = _ptr(x0), c0
+    p.x1, p.c1 = _ptr(x1), c1
+    p.w = _ptr(w)
+    p.out, p.ldo = _ptr(out), out.stride(0)
+    p.n, p.h, p.w_, p.cout = n, h, wd, cout
+    p.dtype = _dt(x0)
+    p.ep = _epilogue(bias, rowvec, h * wd, residual, scale, act)
+    L.check(L.load().mimo_conv3x3(C.byref(p), _stream()), "mimo_conv3x3")
+    _count()
+    return out
+
+
+def im2col3x3(x: torch.Tensor, n: int, h: int, wd: int, *, stride=1, upshift=0, pad_lo=1,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    c = x.shape[1]
+    uh, uw = h << upshift, wd << upshift
+    oh = (uh + 2 * pad_lo - 3 + (0 if pad_lo else 1)) // stride + 1
+    ow = (uw + 2 * pad_lo - 3 + (0 if pad_lo else 1)) // stride + 1
+    if out is None:
+        out = torch.empty((n * oh * ow, 9 * c), dtype=x.dtype, device=x.device)
+    L.check(L.load().mimo_im2col3x3(_ptr(x), _ptr(out), n, h, wd, c, stride, upshift, pad_lo, out.stride(0),
+                                    _dt(x), _stream()), "mimo_im2col3x3")
+    _count()
+    return out
+
+
+def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, hw: int, *, groups=32,
+              eps=1e-5, silu=False, x1: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    c0 = x0.shape[1]
+    c1 = x1.shape[1] if x1 is not None else 0
+    if out is None:
+        out = torch.empty((n * hw, c0 + c1), dtype=x0.dtype, device=x0.device)
+    if stats is None:
+        stats = torch.empty((n * groups * 2,), dtype=torch.float32, device=x0.device)
+    assert x0.is_contiguous() and out.is_contiguous() and stats.numel() >= n * groups * 2
+    p = L.GroupNormParams()
+    p.x0, p.c0 = _ptr(x0), c0
+    p.x1, p.c1 = _ptr(x1), c1
+    p.gamma, p.beta = _ptr(gamma), _ptr(beta)
+    p.out = _ptr(out)
+    p.stats = _ptr(stats)
+    p.n, p.hw, p.groups = n, hw, groups
+    p.eps = float(eps)
+    p.silu = int(bool(silu))
+    p.dtype = _dt(x0)
+    L.check(L.load().mimo_groupnorm(C.byref(p), _stream()), "mimo_groupnorm")
+    _count(2)
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps=1e-5, pe: Optional[torch.Tensor] = None,
+              rows_per_frame=1, frames=1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert x.is_contiguous() and x.dim() == 2
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.load().mimo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), x.shape[0], x.shape[1], float(eps),
+                                    _ptr(pe), int(rows_per_frame), int(frames), _dt(x), _stream()), "mimo_layernorm")
+    _count()
+    return out
+
+
+def attn_spatial(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n: int, lq: int, heads: int, *,
+                 bank_k: Optional[torch.Tensor] = None, bank_v: Optional[torch.Tensor] = None,
+                 bank_index: Optional[torch.Tensor] = None, scale: Optional[float] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q/k/v: [n*lq, C] column slices (views) of one fused buffer; bank_k/v: [nb*lb, C]; bank_index int32 [n]."""
+    Cdim = q.shape[1]
+    d = Cdim // heads
+    assert q.stride(0) == k.stride(0) == v.stride(0) and q.stride(1) == 1
+    if out is None:
+        out = torch.empty((n * lq, Cdim), dtype=q.dtype, device=q.device)
+    p = L.AttnParams()
+    p.q, p.k, p.v, p.ld_qkv = _ptr(q), _ptr(k), _ptr(v), q.stride(0)
+    if bank_k is not None:
+        assert bank_v is not None and bank_index is not None and bank_index.dtype == torch.int32
+        assert bank_k.stride(0) == bank_v.stride(0)
+        nb = 1 if bank_k.dim() == 2 else bank_k.shape[0]
+        p.bank_k, p.bank_v, p.ld_bank = _ptr(bank_k), _ptr(bank_v), bank_k.stride(-2)
+        p.lb = bank_k.shape[-2]
+        p.nb = nb
+        p.bank_index = _ptr(bank_index)
+    else:
+        p.bank_k = p.bank_v = p.bank_index = None
+        p.ld_bank, p.lb, p.nb = 0, 0, 0
+    p.out, p.ld_out = _ptr(out), out.stride(0)
+    p.n, p.lq, p.heads, p.d = n, lq, heads, d
+    p.scale = float(scale if scale is not None else d ** -0.5)
+    p.dtype = _dt(q)
+    L.check(L.load().mimo_attn_spatial(C.byref(p), _stream()), "mimo_attn_spatial")
+    _count()
+    return out
+
+
+def attn_temporal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, frames: int, hw: int, heads: int, *,
+                  scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    Cdim = q.shape[1]
+    d = Cdim // heads
+    if out is None:
+        out = torch.empty((batch * frames * hw, Cdim), dtype=q.dtype, device=q.device)
+    L.check(L.load().mimo_attn_temporal(_ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0), batch, frames,
+                                        hw, heads, d, float(scale if scale is not None else d ** -0.5), _dt(q),
+                                        _stream()), "mimo_attn_temporal")
+    _count()
+    return out
+
+
+def ncfhw_to_nhwc(src: torch.Tensor, cpad: int, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    b, c, f, h, w = src.shape
+    assert src.is_contiguous() and src.dtype in (torch.float32, dtype)
+    if out is None:
+        out = torch.empty((b * f * h * w, cpad), dtype=dtype, device=src.device)
+    L.check(L.load().mimo_ncfhw_to_nhwc(_ptr(src), _ptr(out), b, c, f, h, w, cpad, int(src.dtype == torch.float32),
+                                        _dt(out), _stream()), "mimo_ncfhw_to_nhwc")
+    _count()
+    return out
+
+
+def nhwc_to_ncfhw(src: torch.Tensor, b: int, c: int, f: int, h: int, w: int, *, out_dtype: Optional[torch.dtype] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    out_dtype = out_dtype or src.dtype
+    if out is None:
+        out = torch.empty((b, c, f, h, w), dtype=out_dtype, device=src.device)
+    L.check(L.load().mimo_nhwc_to_ncfhw(_ptr(src), _ptr(out), b, c, f, h, w, src.stride(0),
+                                        int(out.dtype == torch.float32), _dt(src), _stream()), "mimo_nhwc_to_ncfhw")
+    _count()
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty_like(a)
+    L.check(L.load().mimo_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), _dt(a), _stream()), "mimo_add")
+    _count()
+    return out
+
+
+def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.load().mimo_silu(_ptr(x), _ptr(out), x.numel(), _dt(x), _stream()), "mimo_silu")
+    _count()
+    return out
+
+
+def cfg_ddim_step(pred_uncond: torch.Tensor, pred_cond: torch.Tensor, latents: torch.Tensor, guidance: float,
+                  sqrt_a_t: float, sqrt_1ma_t: float, sqrt_a_prev: float, sqrt_1ma_prev: float, *,
+                  counter: Optional[torch.Tensor] = None, frame_stride: int = 0) -> torch.Tensor:
+    """In-place DDIM update of `latents` from the two CFG halves of the (window-accumulated) prediction."""
+    L.check(L.load().mimo_cfg_ddim_step(_ptr(pred_uncond), _ptr(pred_cond), _ptr(counter), int(frame_stride),
+                                        _ptr(latents), latents.numel(), float(guidance), float(sqrt_a_t),
+                                        float(sqrt_1ma_t), float(sqrt_a_prev), float(sqrt_1ma_prev), _dt(latents),
+                                        _stream()), "mimo_cfg_ddim_step")
+    _count()
+    return latents
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing (host side, once per model load)
+# ------------------------------------------------------------------------------------------------
+def pack_conv3x3_weight(w: torch.Tensor, cin_pad: Optional[int] = None, cout_pad: Optional[int] = None) -> torch.Tensor:
+    """OIHW [cout, cin, 3, 3] -> [cout_pad, 9 * cin_pad], K index = (ky*3+kx) * cin_pad + ch."""
+    cout, cin = w.shape[:2]
+    cin_pad = cin_pad or (cin + 7) // 8 * 8
+    cout_pad = cout_pad or (cout + 7) // 8 * 8
+    p = torch.zeros((cout_pad, 9, cin_pad), dtype=w.dtype, device=w.device)
+    p[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    return p.reshape(cout_pad, 9 * cin_pad).contiguous()
+
+
+def pack_geglu_weight(w: torch.Tensor, b: Optional[torch.Tensor]):
+    """diffusers GEGLU proj weight [2*inner, dim] (value rows then gate rows) -> tile-interleaved rows."""
+    n2 = w.shape[0]
+    inner = n2 // 2
+    g = L.load().mimo_gemm_geglu_granule(n2)
+    assert inner % g == 0
+    wv, wg = w[:inner].reshape(inner // g, g, -1), w[inner:].reshape(inner // g, g, -1)
+    wp = torch.stack([wv, wg], dim=1).reshape(n2, -1).contiguous()
+    bp = None
+    if b is not None:
+        bv, bg = b[:inner].reshape(inner // g, g), b[inner:].reshape(inner // g, g)
+        bp = torch.stack([bv, bg], dim=1).reshape(n2).contiguous()
+    return wp, bp
