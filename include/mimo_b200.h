@@ -45,8 +45,9 @@ int mimo_device_check(int dev);
  *                                                      + residual[row][c]) * scale)                      */
 typedef struct {
   const void* bias;       /* [N] or NULL                                                              */
-  const void* rowvec;     /* [ceil(M / rows_per_group), N] or NULL (time embedding / folded cross-attn) */
-  int64_t rows_per_group; /* rows sharing one rowvec row (H*W for per-frame vectors)                   */
+  const void* rowvec;     /* [ceil(M / rows_per_group), ld_rowvec] or NULL (time embedding / folded cross-attn) */
+  int64_t rows_per_group; /* rows sharing one rowvec row (f*H*W for per-CFG-branch vectors)            */
+  int64_t ld_rowvec;      /* row stride of rowvec in elements (0 = N)                                  */
   const void* residual;   /* [M, ld_res] or NULL                                                      */
   int64_t ld_res;
   float scale; /* 1 / output_scale_factor                                                  */
@@ -62,11 +63,14 @@ typedef struct {
 typedef struct {
   const void* a;
   int64_t lda;
+  const void* a1; /* optional second A source: A = [a | a1] along K (virtual concat), or NULL */
+  int64_t lda1;
   const void* w;
   int64_t ldw;
   void* out;
   int64_t ldo;
-  int32_t M, N, K;
+  int32_t M, N, K; /* K = columns of `a`   */
+  int32_t K1;      /* columns of `a1` (0 if a1 == NULL); w is [N, K + K1] */
   int32_t dtype;
   mimo_epilogue ep;
 } mimo_gemm_params;
@@ -168,6 +172,11 @@ int mimo_ncfhw_to_nhwc(const void* src, void* dst, int32_t b, int32_t c, int32_t
 /* [(b f), h, w, ld] channels-last (first c channels) -> [b, c, f, h, w] */
 int mimo_nhwc_to_ncfhw(const void* src, void* dst, int32_t b, int32_t c, int32_t f, int32_t h, int32_t w,
                        int32_t ld, int32_t dst_is_f32, int32_t dtype, void* stream);
+/* nearest-neighbour x2 upsampling of [n, h, w, c] -> [n, 2h, 2w, c] (F.interpolate in Upsample3D, resnet.py:70-73) */
+int mimo_upsample2x(const void* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream);
+/* in-place row softmax of x[rows, cols] (leading dim ld), fp32 math: the VAE mid-block attention (1 head, d=512) is
+ * run as GEMM -> softmax -> GEMM (diffusers AttnProcessor2_0 on UNetMidBlock2D's Attention). */
+int mimo_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t ld, int32_t dtype, void* stream);
 /* out = a + b (same shape, count elements) */
 int mimo_add(const void* a, const void* b, void* out, int64_t count, int32_t dtype, void* stream);
 /* out = silu(x) */

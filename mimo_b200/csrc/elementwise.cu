@@ -99,6 +99,74 @@ __global__ void im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ col, i
   }
 }
 
+// nearest x2 upsample, channels-last: one thread per output (pixel, 8-channel vector)
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int h, int w, int vecs) {
+  const int oh = 2 * h, ow = 2 * w;
+  const long long total = static_cast<long long>(n) * oh * ow * vecs;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % vecs);
+    const long long opix = i / vecs;
+    const int ox = static_cast<int>(opix % ow);
+    const int oy = static_cast<int>((opix / ow) % oh);
+    const long long ni = opix / (static_cast<long long>(ow) * oh);
+    out[i] = x[((ni * h + (oy >> 1)) * w + (ox >> 1)) * vecs + cv];
+  }
+}
+
+// in-place row softmax, one CTA per row, fp32 math
+template <bool kBf16>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(void* __restrict__ xp, int cols, long long ld) {
+  using C = Cvt<kBf16>;
+  using T = typename C::T;
+  __shared__ float red[32];
+  T* row = static_cast<T*>(xp) + static_cast<long long>(blockIdx.x) * ld;
+  const int vecs = cols / 8;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(row)[v];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = C::unpack(w[j]);
+      m = fmaxf(m, fmaxf(t.x, t.y));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(row)[v];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = C::unpack(w[j]);
+      s += __expf(t.x - m) + __expf(t.y - m);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) s += red[i];
+  const float inv = 1.0f / s;
+  for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(row)[v];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = C::unpack(w[j]);
+      o[j] = C::pack(__expf(t.x - m) * inv, __expf(t.y - m) * inv);
+    }
+    reinterpret_cast<uint4*>(row)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 template <bool kBf16, int kOp>  // 0: add, 1: silu
 __global__ void ew_kernel(const void* __restrict__ a, const void* __restrict__ b, void* __restrict__ out,
                           long long nvec) {
@@ -238,6 +306,31 @@ extern "C" int mimo_im2col3x3(const void* x, void* col, int32_t n, int32_t h, in
       static_cast<const uint16_t*>(x), static_cast<uint16_t*>(col), n, h, w, c, stride, upshift, pad_lo, oh, ow,
       ldcol);
   MIMO_CHECK_LAUNCH("im2col3x3 launch");
+  return MIMO_OK;
+}
+
+extern "C" int mimo_upsample2x(const void* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t dtype,
+                               void* stream) {
+  (void)dtype;
+  if (!x || !out || n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8)) return set_error(MIMO_ERR_ARG, "mimo_upsample2x: bad arguments");
+  if (int rc = ensure_device()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<ew_grid(total, 256), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), n, h, w, c / 8);
+  MIMO_CHECK_LAUNCH("upsample2x launch");
+  return MIMO_OK;
+}
+
+extern "C" int mimo_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t ld, int32_t dtype, void* stream) {
+  if (!x || rows <= 0 || cols <= 0 || (cols % 8) || (ld % 8) || rows > 0x7fffffffLL)
+    return set_error(MIMO_ERR_ARG, "mimo_softmax_rows: bad arguments");
+  if (int rc = ensure_device()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MIMO_BF16)
+    softmax_rows_kernel<true><<<static_cast<unsigned>(rows), 256, 0, st>>>(x, cols, ld);
+  else
+    softmax_rows_kernel<false><<<static_cast<unsigned>(rows), 256, 0, st>>>(x, cols, ld);
+  MIMO_CHECK_LAUNCH("softmax_rows launch");
   return MIMO_OK;
 }
 

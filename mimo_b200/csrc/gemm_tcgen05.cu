@@ -32,6 +32,7 @@ struct EpiArgs {
   const void* residual;
   void* out;
   long long rows_per_group;
+  long long ld_rowvec;
   long long ld_res;
   long long ldo;
   float scale;
@@ -120,8 +121,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         uint8_t* sb = sa + BM * BK * 2;
         if (!g.conv) {
           mbar_expect_tx(&full_bar[stage], BM * BK * 2 + BN * BK * 2);
-          tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, m_tile * BM);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
+          if (kb < g.kb0) {  // A = [A0 | A1] along K (virtual concat for the up-block shortcut GEMMs)
+            tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, m_tile * BM);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
+          } else {
+            tma_load_2d(sa, &tmA1, &full_bar[stage], (kb - g.kb0) * BK, m_tile * BM);
+            tma_load_2d(sb, &tmB, &full_bar[stage], g.c0 + (kb - g.kb0) * BK, n_tile * BN);
+          }
         } else {
           const int tap = kb / kb_per_tap;
           const int rem = kb - tap * kb_per_tap;
@@ -224,7 +230,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 }
                 if (ep.rowvec) {
                   const uint4 b = __ldg(reinterpret_cast<const uint4*>(
-                      static_cast<const typename C::T*>(ep.rowvec) + grp * N + col));
+                      static_cast<const typename C::T*>(ep.rowvec) + grp * ep.ld_rowvec + col));
                   const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
@@ -384,17 +390,19 @@ int pick_bn(int N, bool geglu, long long m_tiles) {
   return best;
 }
 
-static EpiArgs make_epi(const mimo_epilogue& e, void* out, long long ldo) {
+static EpiArgs make_epi(const mimo_epilogue& e, void* out, long long ldo, int N) {
   EpiArgs a;
   a.bias = e.bias;
   a.rowvec = e.rowvec;
   a.residual = e.residual;
   a.out = out;
   a.rows_per_group = e.rows_per_group > 0 ? e.rows_per_group : 1;
+  a.ld_rowvec = e.ld_rowvec;
   a.ld_res = e.ld_res;
   a.ldo = ldo;
   a.scale = e.scale;
   a.act = e.act;
+  if (a.ld_rowvec <= 0) a.ld_rowvec = N;
   return a;
 }
 
@@ -421,23 +429,36 @@ extern "C" int mimo_gemm(const mimo_gemm_params* p, void* stream) {
   const int bn = pick_bn(p->N, geglu, mt);
   if (geglu && (p->N % bn)) return set_error(MIMO_ERR_ARG, "mimo_gemm: GEGLU needs N % tile == 0");
   const int nt = (p->N + bn - 1) / bn;
-  const int nkb = (p->K + BK - 1) / BK;
+  const int K1 = p->a1 ? p->K1 : 0;
+  if (K1 < 0 || (K1 % 8) || (p->a1 && (p->lda1 % 8))) return set_error(MIMO_ERR_ARG, "mimo_gemm: K1/lda1 % 8 != 0");
+  const int kb0 = (p->K + BK - 1) / BK;
+  const int kb1 = (K1 + BK - 1) / BK;
+  const int nkb = kb0 + kb1;
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, ta1, tb;
   const uint64_t adim[2] = {static_cast<uint64_t>(p->K), static_cast<uint64_t>(p->M)};
   const uint64_t astr[1] = {static_cast<uint64_t>(p->lda) * 2};
   const uint32_t abox[2] = {BK, BM};
   if (int rc = encode_tmap(&ta, p->dtype, 2, p->a, adim, astr, abox)) return rc;
-  const uint64_t bdim[2] = {static_cast<uint64_t>(p->K), static_cast<uint64_t>(p->N)};
+  ta1 = ta;
+  if (K1) {
+    const uint64_t a1dim[2] = {static_cast<uint64_t>(K1), static_cast<uint64_t>(p->M)};
+    const uint64_t a1str[1] = {static_cast<uint64_t>(p->lda1) * 2};
+    if (int rc = encode_tmap(&ta1, p->dtype, 2, p->a1, a1dim, a1str, abox)) return rc;
+  }
+  const uint64_t bdim[2] = {static_cast<uint64_t>(p->K + K1), static_cast<uint64_t>(p->N)};
   const uint64_t bstr[1] = {static_cast<uint64_t>(p->ldw) * 2};
   const uint32_t bbox[2] = {BK, static_cast<uint32_t>(bn)};
   if (int rc = encode_tmap(&tb, p->dtype, 2, p->w, bdim, bstr, bbox)) return rc;
 
   ConvGeom g = {};
-  EpiArgs ep = make_epi(p->ep, p->out, p->ldo);
+  g.kb0 = kb0;
+  g.kb1 = kb1;
+  g.c0 = p->K;
+  EpiArgs ep = make_epi(p->ep, p->out, p->ldo, p->N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == MIMO_BF16) return launch_bn<true>(bn, ta, ta, tb, p->M, p->N, mt, nt, nkb, g, ep, st);
-  return launch_bn<false>(bn, ta, ta, tb, p->M, p->N, mt, nt, nkb, g, ep, st);
+  if (p->dtype == MIMO_BF16) return launch_bn<true>(bn, ta, ta1, tb, p->M, p->N, mt, nt, nkb, g, ep, st);
+  return launch_bn<false>(bn, ta, ta1, tb, p->M, p->N, mt, nt, nkb, g, ep, st);
 }
 
 extern "C" int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream) {
@@ -505,7 +526,7 @@ extern "C" int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream) {
     const uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
     if (int rc = encode_tmap(&tb, p->dtype, 2, p->w, dim, str, box)) return rc;
   }
-  EpiArgs ep = make_epi(p->ep, p->out, p->ldo);
+  EpiArgs ep = make_epi(p->ep, p->out, p->ldo, p->cout);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dtype == MIMO_BF16)
     return launch_bn<true>(bn, ta0, ta1, tb, static_cast<int>(Mrows), p->cout, mt, nt, nkb, g, ep, st);

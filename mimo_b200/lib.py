@@ -25,6 +25,7 @@ class Epilogue(C.Structure):
         ("bias", C.c_void_p),
         ("rowvec", C.c_void_p),
         ("rows_per_group", C.c_int64),
+        ("ld_rowvec", C.c_int64),
         ("residual", C.c_void_p),
         ("ld_res", C.c_int64),
         ("scale", C.c_float),
@@ -35,9 +36,10 @@ class Epilogue(C.Structure):
 class GemmParams(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("lda", C.c_int64),
+        ("a1", C.c_void_p), ("lda1", C.c_int64),
         ("w", C.c_void_p), ("ldw", C.c_int64),
         ("out", C.c_void_p), ("ldo", C.c_int64),
-        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("K1", C.c_int32),
         ("dtype", C.c_int32),
         ("ep", Epilogue),
     ]
@@ -98,6 +100,8 @@ SYMBOLS = {
     "mimo_attn_temporal": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _F, _I32, _VP]),
     "mimo_ncfhw_to_nhwc": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "mimo_nhwc_to_ncfhw": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "mimo_upsample2x": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "mimo_softmax_rows": (C.c_int, [_VP, _I64, _I32, _I64, _I32, _VP]),
     "mimo_add": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _VP]),
     "mimo_silu": (C.c_int, [_VP, _VP, _I64, _I32, _VP]),
     "mimo_cfg_ddim_step": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _I64, _F, _F, _F, _F, _F, _I32, _VP]),

@@ -49,6 +49,7 @@ def _epilogue(bias=None, rowvec=None, rows_per_group=1, residual=None, scale=1.0
     ep.bias = _ptr(bias)
     ep.rowvec = _ptr(rowvec)
     ep.rows_per_group = int(rows_per_group)
+    ep.ld_rowvec = rowvec.stride(0) if rowvec is not None else 0
     ep.residual = _ptr(residual)
     ep.ld_res = residual.stride(0) if residual is not None else 0
     ep.scale = float(scale)
@@ -56,10 +57,11 @@ def _epilogue(bias=None, rowvec=None, rows_per_group=1, residual=None, scale=1.0
     return ep
 
 
-def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, rowvec=None,
-         rows_per_group=1, residual=None, scale=1.0, act=L.ACT_NONE) -> torch.Tensor:
-    """out[M, N(or N/2 for GEGLU)] = epilogue(a[M, K] @ w[N, K]^T)."""
-    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, a1: Optional[torch.Tensor] = None,
+         bias=None, rowvec=None, rows_per_group=1, residual=None, scale=1.0, act=L.ACT_NONE) -> torch.Tensor:
+    """out[M, N(or N/2 for GEGLU)] = epilogue([a | a1][M, K + K1] @ w[N, K + K1]^T)."""
+    K1 = a1.shape[1] if a1 is not None else 0
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] + K1 == w.shape[1]
     assert a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
     N = w.shape[0]
@@ -69,6 +71,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *
     assert out.shape == (M, n_out) and out.stride(1) == 1
     p = L.GemmParams()
     p.a, p.lda = _ptr(a), a.stride(0)
+    p.a1, p.lda1, p.K1 = (_ptr(a1), a1.stride(0), K1) if a1 is not None else (None, 0, 0)
     p.w, p.ldw = _ptr(w), w.stride(0)
     p.out, p.ldo = _ptr(out), out.stride(0)
     p.M, p.N, p.K = M, N, K
@@ -80,8 +83,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *
 
 
 def conv3x3(x0: torch.Tensor, w: torch.Tensor, n: int, h: int, wd: int, out: Optional[torch.Tensor] = None, *,
-            x1: Optional[torch.Tensor] = None, bias=None, rowvec=None, residual=None, scale=1.0,
-            act=L.ACT_NONE) -> torch.Tensor:
+            x1: Optional[torch.Tensor] = None, bias=None, rowvec=None, rows_per_group: Optional[int] = None,
+            residual=None, scale=1.0, act=L.ACT_NONE) -> torch.Tensor:
     """3x3/s1/p1 conv over channels-last x0 [n*h*wd, c0] (+ x1 [n*h*wd, c1]); w packed [cout, 9*(c0+c1)]."""
     c0 = x0.shape[1]
     c1 = x1.shape[1] if x1 is not None else 0
@@ -97,7 +100,7 @@ def conv3x3(x0: torch.Tensor, w: torch.Tensor, n: int, h: int, wd: int, out: Opt
     p.out, p.ldo = _ptr(out), out.stride(0)
     p.n, p.h, p.w_, p.cout = n, h, wd, cout
     p.dtype = _dt(x0)
-    p.ep = _epilogue(bias, rowvec, h * wd, residual, scale, act)
+    p.ep = _epilogue(bias, rowvec, rows_per_group or h * wd, residual, scale, act)
     L.check(L.load().mimo_conv3x3(C.byref(p), _stream()), "mimo_conv3x3")
     _count()
     return out
@@ -218,6 +221,23 @@ def nhwc_to_ncfhw(src: torch.Tensor, b: int, c: int, f: int, h: int, w: int, *, 
                                         int(out.dtype == torch.float32), _dt(src), _stream()), "mimo_nhwc_to_ncfhw")
     _count()
     return out
+
+
+def upsample2x(x: torch.Tensor, n: int, h: int, w: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    c = x.shape[1]
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty((n * 4 * h * w, c), dtype=x.dtype, device=x.device)
+    L.check(L.load().mimo_upsample2x(_ptr(x), _ptr(out), n, h, w, c, _dt(x), _stream()), "mimo_upsample2x")
+    _count()
+    return out
+
+
+def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
+    assert x.dim() == 2 and x.stride(1) == 1
+    L.check(L.load().mimo_softmax_rows(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _dt(x), _stream()), "mimo_softmax_rows")
+    _count()
+    return x
 
 
 def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -26,6 +26,14 @@ import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
 
+TAPS: Optional[dict] = None  # debugging aid: when a dict, _unet_body records every block output [N, C, H, W] by path
+
+
+def _tap(name: str, x: torch.Tensor) -> torch.Tensor:
+    if TAPS is not None:
+        TAPS[name] = x.detach().float().cpu()
+    return x
+
 
 # =====================================================================================================
 # configuration (configs/inference/inference_v2.yaml + SD1.5 unet/config.json)
@@ -249,32 +257,32 @@ def _unet_body(sd: SD, x: torch.Tensor, temb: torch.Tensor, cfg_: UNetConfig, xf
     for i in range(nb):
         has_attn = i < nb - 1
         for j in range(cfg_.layers_per_block):
-            x = resnet_block(sd, f"down_blocks.{i}.resnets.{j}", x, temb, g, eps)
+            x = _tap(f"down_blocks.{i}.resnets.{j}", resnet_block(sd, f"down_blocks.{i}.resnets.{j}", x, temb, g, eps))
             if has_attn:
-                x = xf_fn(f"down_blocks.{i}.attentions.{j}", x)
+                x = _tap(f"down_blocks.{i}.attentions.{j}", xf_fn(f"down_blocks.{i}.attentions.{j}", x))
             if mm_fn is not None:
-                x = mm_fn(f"down_blocks.{i}.motion_modules.{j}", x)
+                x = _tap(f"down_blocks.{i}.motion_modules.{j}", mm_fn(f"down_blocks.{i}.motion_modules.{j}", x))
             skips.append(x)
         if i < nb - 1:
-            x = _conv(sd, f"down_blocks.{i}.downsamplers.0.conv", x, stride=2, padding=1)
+            x = _tap(f"down_blocks.{i}.down", _conv(sd, f"down_blocks.{i}.downsamplers.0.conv", x, stride=2, padding=1))
             skips.append(x)
-    x = resnet_block(sd, "mid_block.resnets.0", x, temb, g, eps)
-    x = xf_fn("mid_block.attentions.0", x)
+    x = _tap("mid_block.resnets.0", resnet_block(sd, "mid_block.resnets.0", x, temb, g, eps))
+    x = _tap("mid_block.attentions.0", xf_fn("mid_block.attentions.0", x))
     if mm_fn is not None:
-        x = mm_fn("mid_block.motion_modules.0", x)
-    x = resnet_block(sd, "mid_block.resnets.1", x, temb, g, eps)
+        x = _tap("mid_block.motion_modules.0", mm_fn("mid_block.motion_modules.0", x))
+    x = _tap("mid_block.resnets.1", resnet_block(sd, "mid_block.resnets.1", x, temb, g, eps))
     for i in range(nb):
         has_attn = i > 0
         for j in range(cfg_.layers_per_block + 1):
             x = torch.cat([x, skips.pop()], dim=1)
-            x = resnet_block(sd, f"up_blocks.{i}.resnets.{j}", x, temb, g, eps)
+            x = _tap(f"up_blocks.{i}.resnets.{j}", resnet_block(sd, f"up_blocks.{i}.resnets.{j}", x, temb, g, eps))
             if has_attn:
-                x = xf_fn(f"up_blocks.{i}.attentions.{j}", x)
+                x = _tap(f"up_blocks.{i}.attentions.{j}", xf_fn(f"up_blocks.{i}.attentions.{j}", x))
             if mm_fn is not None:
-                x = mm_fn(f"up_blocks.{i}.motion_modules.{j}", x)
+                x = _tap(f"up_blocks.{i}.motion_modules.{j}", mm_fn(f"up_blocks.{i}.motion_modules.{j}", x))
         if i < nb - 1:
             x = F.interpolate(x, scale_factor=2.0, mode="nearest")  # Upsample3D: scale_factor=[1,2,2] over (f,h,w)
-            x = _conv(sd, f"up_blocks.{i}.upsamplers.0.conv", x)
+            x = _tap(f"up_blocks.{i}.up", _conv(sd, f"up_blocks.{i}.upsamplers.0.conv", x))
     return x
 
 

@@ -373,7 +373,104 @@ def perf():
     return True
 
 
-CHECKS = {f.__name__: f for f in [gemm_basic, gemm_shapes, gemm_persistent, gemm_epilogue, conv_basic, conv_shapes,
+def _oracle():
+    from oracle import torch_oracle as O
+    return O
+
+
+def _unet_parity(cfg_widths, f, hw, seed, taps=True, tol=3e-2):
+    """engine (fp16 kernels) vs oracle (fp32 torch on the GPU, TF32 off) on one CFG window, block by block."""
+    from mimo_b200 import engine as E
+    O = _oracle()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.UNetConfig(block_out_channels=cfg_widths)
+    sd_den = O.make_denoising_unet_sd(cfg, seed=seed)
+    sd_ref = O.make_reference_unet_sd(cfg, seed=seed + 1)
+    sd_pg = O.make_pose_guider_sd(seed=seed + 2, out_channels=cfg.block_out_channels[0])
+    g = torch.Generator().manual_seed(seed + 10)
+    ref_lat = torch.randn(1, 4, hw, hw, generator=g)
+    emb = torch.randn(1, 1, cfg.cross_attention_dim, generator=g)
+    ehs = torch.cat([torch.zeros_like(emb), emb])
+    x = torch.randn(1, 8, f, hw, hw, generator=g).repeat(2, 1, 1, 1, 1)
+    pose_img = torch.rand(1, 3, f, hw * 8, hw * 8, generator=g)
+    t = 499
+    dev = torch.device(DEV)
+    # oracle: fp32 weights rounded to fp16 first (the engine stores fp16 weights), math in fp32
+    r16 = lambda sd: {k: v.half().float().to(dev) for k, v in sd.items()}
+    o_den, o_ref, o_pg = r16(sd_den), r16(sd_ref), r16(sd_pg)
+    with torch.no_grad():
+        banks = O.reference_unet_banks(o_ref, ref_lat.repeat(2, 1, 1, 1).half().float().to(dev), ehs.half().float().to(dev), cfg)
+        pose_o = O.pose_guider(o_pg, pose_img.half().float().to(dev))
+        O.TAPS = {} if taps else None
+        want = O.denoising_unet(o_den, x.half().float().to(dev), t, ehs.half().float().to(dev),
+                                pose_o.repeat(2, 1, 1, 1, 1), banks, cfg, cfg=True)
+        otaps, O.TAPS = O.TAPS, None
+    spec = E.UNetSpec(block_out_channels=cfg_widths)
+    den = E.UNetEngine(sd_den, spec, dev)
+    ref = E.UNetEngine(sd_ref, E.UNetSpec(block_out_channels=cfg_widths, in_channels=4, motion=False, out_head=False), dev)
+    pg = E.PoseGuiderEngine(sd_pg, dev)
+    ok = True
+    pose_e = pg.forward(pose_img.half().to(dev))
+    pose_e5 = pose_e.reshape(1, f, hw, hw, -1).permute(0, 4, 1, 2, 3)
+    ok &= report("pose_guider engine", pose_e5, pose_o, tol=5e-3)
+    ebanks = ref.write_banks(ref_lat.repeat(2, 1, 1, 1).half().to(dev), ehs.half().to(dev), den)
+    # compare one projected bank against the oracle's bank features pushed through the reader's to_k
+    p0 = den.xf_paths[0]
+    C0 = den.w[p0]["C"]
+    wk = o_den[p0 + ".transformer_blocks.0.attn1.to_k.weight"]
+    ok &= report(f"bank K {p0}", ebanks[p0][:, :, :C0], banks[p0].float() @ wk.t(), tol=5e-3)
+    plast = [p for p in den.xf_paths if p.startswith("up_blocks")][-1]
+    Cl = den.w[plast]["C"]
+    wkl = o_den[plast + ".transformer_blocks.0.attn1.to_k.weight"]
+    ok &= report(f"bank K {plast}", ebanks[plast][:, :, :Cl], banks[plast].float() @ wkl.t(), tol=3e-2)
+    den.begin_clip(ehs.half().to(dev), ebanks, cfg=True, frames=f)
+    den.taps = {} if taps else None
+    pose_rep = pose_e.reshape(1, f * hw * hw, -1).repeat(2, 1, 1).reshape(2 * f * hw * hw, -1).contiguous()
+    got = den.forward(x.half().to(dev), t, pose_rep)
+    torch.cuda.synchronize()
+    if taps:
+        for name, ov in otaps.items():
+            if name in den.taps:
+                e = rel_err(den.taps[name], ov)
+                flag = "" if e < tol else "   <<<<<<"
+                print(f"    tap {name:40s} rel_l2={e:.3e}{flag}")
+    ok &= report(f"denoising_unet widths={cfg_widths} f={f} latent={hw}", got, want, tol=tol)
+    return ok
+
+
+def unet_small():
+    return _unet_parity((128, 256, 512, 512), f=4, hw=16, seed=100)
+
+
+def unet_full():
+    return _unet_parity((320, 640, 1280, 1280), f=4, hw=32, seed=400)
+
+
+def vae_parity():
+    from mimo_b200 import engine as E
+    O = _oracle()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device(DEV)
+    ok = True
+    for widths, hw, n in [((32, 64, 128, 128), 16, 2), ((128, 256, 512, 512), 32, 2)]:
+        if widths[0] < 128:
+            continue  # 32 groups need >= 4 channels per group in the GN kernel
+        cfg = O.VAEConfig(block_out_channels=widths)
+        sd = O.make_vae_sd(cfg, seed=7)
+        z = torch.randn(n, 4, hw, hw, generator=torch.Generator().manual_seed(8)) * 3
+        o_sd = {k: v.half().float().to(dev) for k, v in sd.items()}
+        with torch.no_grad():
+            want = O.vae_decode(o_sd, z.half().float().to(dev), cfg)
+        eng = E.VAEDecoderEngine(sd, dev)
+        got = eng.decode(z.half().to(dev))
+        torch.cuda.synchronize()
+        ok &= report(f"vae_decode widths={widths} latent={hw}", got, want, tol=2e-2)
+    return ok
+
+
+CHECKS = {f.__name__: f for f in [unet_small, unet_full, vae_parity,gemm_basic, gemm_shapes, gemm_persistent, gemm_epilogue, conv_basic, conv_shapes,
                                   norms, temporal, spatial_basic, spatial_shapes, elementwise, perf]}
 
 if __name__ == "__main__":
