@@ -40,6 +40,9 @@ const char* mimo_version(void);
 const char* mimo_last_error(void);
 /* 0 if device `dev` is sm_100; MIMO_ERR_DEVICE otherwise (also when there is no CUDA device at all). */
 int mimo_device_check(int dev);
+/* sizeof() of the parameter structs as compiled into the library (0 epilogue, 1 gemm, 2 conv3x3, 3 groupnorm,
+ * 4 attn): lets a binding verify its struct mirrors before the first call. */
+int mimo_abi_sizeof(int which);
 
 /* Fused epilogue shared by GEMM and conv:  out = act((acc + bias[c] + rowvec[row / rows_per_group][c]
  *                                                      + residual[row][c]) * scale)                      */

@@ -91,6 +91,17 @@ int encode_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const u
 extern "C" const char* mimo_version(void) { return "mimo_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* mimo_last_error(void) { return mimo::g_err; }
 
+extern "C" int mimo_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return static_cast<int>(sizeof(mimo_epilogue));
+    case 1: return static_cast<int>(sizeof(mimo_gemm_params));
+    case 2: return static_cast<int>(sizeof(mimo_conv3x3_params));
+    case 3: return static_cast<int>(sizeof(mimo_groupnorm_params));
+    case 4: return static_cast<int>(sizeof(mimo_attn_params));
+  }
+  return -1;
+}
+
 extern "C" int mimo_device_check(int dev) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);

@@ -227,7 +227,8 @@ class UNetEngine:
         bank = st["banks"].get(p)
         if bank is not None:
             att = ops.attn_spatial(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], n, hw, self.spec.heads,
-                                   bank_k=bank[:, :, :C], bank_v=bank[:, :, C:], bank_index=st["bank_index"])
+                                   bank_k=bank[:, :, :C], bank_v=bank[:, :, C:], bank_index=st["bank_index"],
+                                   n_bank_frames=(n // 2 if st["cfg"] else n))
         else:
             att = ops.attn_spatial(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], n, hw, self.spec.heads)
         hcur = ops.gemm(att, m["o1"][0], bias=m["o1"][1], residual=hcur, rowvec=st["xattn"][p],
@@ -259,7 +260,7 @@ class UNetEngine:
         u = ops.upsample2x(x, n, h, w)
         return ops.conv3x3(u, wp, n, 2 * h, 2 * w, bias=b)
 
-    taps: Optional[dict] = None  # debugging aid (tools/gpu_probe.py): block outputs as [N, C, H, W] fp32 on CPU
+    taps: Optional[dict] = None  # debugging aid (scripts/gpu_probe.py): block outputs as [N, C, H, W] fp32 on CPU
 
     def _tap(self, name, x, n, h, w):
         if self.taps is not None:

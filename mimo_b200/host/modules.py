@@ -69,7 +69,7 @@ class _EngineModel(nn.Module):
                 for s in shp[1:]:
                     fan_in *= s
                 t, buf = torch.randn(shp, generator=gen) / math.sqrt(fan_in), False
-            nn.Module.__getattribute__(self, "_tree").put(parts, t, buf)
+            self._tree.put(parts, t, buf)
 
     def __init__(self):
         super().__init__()
@@ -354,3 +354,35 @@ class ReferenceAttentionControl:
             eng.clip_state = None
         if self.mode == "write":
             self.unet._pending = None
+
+
+class AutoencoderKL(_EngineModel):
+    """Stand-in for diffusers.AutoencoderKL (sd-vae-ft-mse) [3P] with the surface the pipeline touches:
+    .config.block_out_channels, .encode(x).latent_dist.mean, .decode(z).sample, .dtype/.device, state_dict in the
+    diffusers key layout. A real diffusers AutoencoderKL can be passed to the pipeline instead: only its state_dict
+    and config are read."""
+
+    def __init__(self, block_out_channels=(128, 256, 512, 512), layers_per_block=2, latent_channels=4, in_channels=3,
+                 out_channels=3, norm_num_groups=32, scaling_factor=0.18215, **unused):
+        super().__init__()
+        self.config = SimpleNamespace(block_out_channels=tuple(block_out_channels), layers_per_block=layers_per_block,
+                                      latent_channels=latent_channels, norm_num_groups=norm_num_groups,
+                                      scaling_factor=scaling_factor)
+        self._materialise(schema.vae_schema(block_out_channels, layers_per_block, latent_channels, in_channels,
+                                            out_channels))
+
+    def engine(self):
+        self._require_cuda()
+        if self._engine is None or self._engine_key != self._key():
+            sd = self.state_dict()
+            g = self.config.norm_num_groups
+            self._engine = (E.VAEEncoderEngine(sd, self.device, self.dtype, g), E.VAEDecoderEngine(sd, self.device, self.dtype, g))
+            self._engine_key = self._key()
+        return self._engine
+
+    def encode(self, x):
+        mean = self.engine()[0].encode_mean(x)
+        return SimpleNamespace(latent_dist=SimpleNamespace(mean=mean))
+
+    def decode(self, z):
+        return SimpleNamespace(sample=self.engine()[1].decode(z))

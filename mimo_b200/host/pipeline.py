@@ -1,0 +1,255 @@
+"""Pose2VideoPipeline with the reference's call surface (src/pipelines/pipeline_pose2vid_long_edit_bkfill_roiclip.py:
+36-80 constructor, :338-363 __call__ signature, :573-578 output), driving the sm_100a engine.
+
+What stays as in the reference: PIL pre-processing semantics, CLIP through the HF module the caller passes, the CPU
+generator noise (prepare_latents :149-183), context windows (:492-510), CFG (:545-549) and DDIM (:551-553) maths.
+What changes is where the arithmetic runs: reference_unet / pose_guider / denoising_unet / VAE are engine objects
+behind the C ABI; the CFG + DDIM update is one fused kernel; all frames are decoded in one batched VAE pass.
+
+__call__ = preprocess() [host: PIL -> pinned tensors]  ->  H2D  ->  sample_tensors() [device]  ->  D2H.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Union
+
+import numpy as np
+import PIL.Image
+import torch
+
+from .. import engine as E
+from .. import ops
+from ..lib import MimoError
+from .context import get_context_scheduler
+from .modules import ReferenceAttentionControl
+
+
+@dataclass
+class Pose2VideoPipelineOutput:
+    videos: Union[torch.Tensor, np.ndarray]
+
+
+def pil_to_tensor(images, height: int, width: int, normalize: bool, scale_factor: int = 8) -> torch.Tensor:
+    """diffusers VaeImageProcessor(do_convert_rgb=True).preprocess [3P] as used at pipeline :73-80, :424-426, :436,
+    :448-450: RGB -> LANCZOS resize to (w, h) floored to multiples of 8 -> [0, 1] -> NCHW -> 2x - 1 if normalize."""
+    imgs = images if isinstance(images, (list, tuple)) else [images]
+    w, h = width - width % scale_factor, height - height % scale_factor
+    arr = np.stack([np.asarray(i.convert("RGB").resize((w, h), resample=PIL.Image.LANCZOS), dtype=np.float32) / 255.0
+                    for i in imgs])
+    t = torch.from_numpy(arr).permute(0, 3, 1, 2).contiguous()
+    return 2.0 * t - 1.0 if normalize else t
+
+
+class Pose2VideoPipeline:
+    _optional_components: list = []
+
+    def __init__(self, vae, image_encoder, reference_unet, denoising_unet, pose_guider, scheduler,
+                 image_proj_model=None, tokenizer=None, text_encoder=None):
+        self.vae, self.image_encoder = vae, image_encoder
+        self.reference_unet, self.denoising_unet, self.pose_guider = reference_unet, denoising_unet, pose_guider
+        self.scheduler = scheduler
+        self.image_proj_model, self.tokenizer, self.text_encoder = image_proj_model, tokenizer, text_encoder
+        self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)
+        self._clip_image_processor = None
+        self._vae_engines = None
+        self.timings: Dict[str, float] = {}
+        self.last_latents: Optional[torch.Tensor] = None
+        self.io_bytes = {"h2d": 0, "d2h": 0}
+
+    # ------------------------------------------------------------------------------------------------
+    def to(self, device=None, dtype=None):
+        for m in (self.vae, self.image_encoder, self.reference_unet, self.denoising_unet, self.pose_guider):
+            if isinstance(m, torch.nn.Module):
+                m.to(device=device, dtype=dtype)
+        self._vae_engines = None
+        return self
+
+    @property
+    def device(self) -> torch.device:
+        return self.denoising_unet.device
+
+    def _clip_pixels(self, ref_image: PIL.Image.Image) -> torch.Tensor:
+        if self._clip_image_processor is None:
+            from transformers import CLIPImageProcessor
+            self._clip_image_processor = CLIPImageProcessor()
+        return self._clip_image_processor.preprocess(ref_image.resize((224, 224)), return_tensors="pt").pixel_values
+
+    def _clip_embeds(self, ref_image: PIL.Image.Image) -> torch.Tensor:
+        p = next(self.image_encoder.parameters())
+        return self.image_encoder(self._clip_pixels(ref_image).to(p.device, dtype=p.dtype)).image_embeds
+
+    def _vae(self):
+        from .modules import AutoencoderKL as _OurVAE
+        if isinstance(self.vae, _OurVAE):
+            return self.vae.engine()
+        if self._vae_engines is None:
+            # a diffusers.AutoencoderKL (or anything with its state-dict layout): only weights and config are read
+            sd = self.vae.state_dict()
+            dt = self.denoising_unet.dtype
+            self._vae_engines = (E.VAEEncoderEngine(sd, self.device, dt), E.VAEDecoderEngine(sd, self.device, dt))
+        return self._vae_engines
+
+    def decode_latents_device(self, latents: torch.Tensor) -> torch.Tensor:
+        """[1, 4, F, h, w] -> device tensor [1, 3, F, H, W] in [0, 1] (pipeline :113-123), one batched engine pass."""
+        z = (1 / 0.18215 * latents)[0].permute(1, 0, 2, 3).contiguous()
+        frames = self._vae()[1].decode(z)  # [F, 3, H, W]
+        video = frames.permute(1, 0, 2, 3).unsqueeze(0)
+        return (video / 2 + 0.5).clamp(0, 1)
+
+    def decode_latents(self, latents: torch.Tensor) -> np.ndarray:
+        return self.decode_latents_device(latents).cpu().float().numpy()  # :124-126
+
+    def prepare_latents(self, batch_size, num_channels_latents, width, height, video_length, dtype, device, generator,
+                        latents=None):
+        shape = (batch_size, num_channels_latents, video_length, height // self.vae_scale_factor,
+                 width // self.vae_scale_factor)
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
+                             f"effective batch size of {batch_size}.")
+        if latents is None:
+            # randn_tensor [3P]: a CPU generator draws on the CPU in the target dtype, then moves (pipeline :175-177)
+            gdev = "cpu" if generator is None or generator.device.type == "cpu" else device
+            latents = torch.randn(shape, generator=generator, device=gdev, dtype=dtype)
+        return latents * self.scheduler.init_noise_sigma
+
+    # ------------------------------------------------------------------------------------------------
+    def preprocess(self, ref_image, pose_images, vid_bk_images, width, height, video_length, generator,
+                   dtype) -> Dict[str, torch.Tensor]:
+        """Host side of __call__: PIL -> pinned CPU tensors (what the reference does at pipeline :379-381, :409-418,
+        :424-426, :435-437, :446-453 before anything touches the device)."""
+        pin = lambda t: t.contiguous().pin_memory() if torch.cuda.is_available() else t.contiguous()
+        bk = pil_to_tensor(list(vid_bk_images), height, width, normalize=True)
+        # identical background frames (animate mode: every frame white, run_animate.py:174-177) are encoded once
+        uniq, inverse = torch.unique(bk.flatten(1), dim=0, return_inverse=True)
+        first = torch.stack([(inverse == i).nonzero()[0, 0] for i in range(uniq.shape[0])])
+        pose = pil_to_tensor(list(pose_images), height, width, normalize=False)  # [F, 3, H, W] in [0, 1]
+        return {
+            "clip_pixels": pin(self._clip_pixels(ref_image)),
+            "ref": pin(pil_to_tensor(ref_image, height, width, normalize=True).to(dtype)),
+            "bk_unique": pin(bk[first].to(dtype)),
+            "bk_inverse": inverse,
+            "pose": pin(pose.permute(1, 0, 2, 3).unsqueeze(0).to(dtype)),
+            "latents": pin(self.prepare_latents(1, 4, width, height, video_length, dtype, "cpu", generator)),
+        }
+
+    @torch.no_grad()
+    def sample_tensors(self, inp: Dict[str, torch.Tensor], num_inference_steps: int, guidance_scale: float,
+                       context_schedule="uniform", context_frames=24, context_stride=1, context_overlap=4,
+                       callback=None, callback_steps=1, decode: bool = True) -> Dict[str, torch.Tensor]:
+        """Device side: everything in `inp` already lives in HBM; returns device tensors."""
+        device = self.device
+        dtype = self.denoising_unet.dtype
+        do_cfg = guidance_scale > 1.0
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        marks = [("start", ev())]
+        marks[0][1].record()
+
+        def mark(name):
+            e = ev()
+            e.record()
+            marks.append((name, e))
+
+        self.scheduler.set_timesteps(num_inference_steps, device="cpu")
+        timesteps = [int(t) for t in self.scheduler.timesteps]
+
+        p = next(self.image_encoder.parameters())
+        emb = self.image_encoder(inp["clip_pixels"].to(p.device, dtype=p.dtype)).image_embeds.to(dtype)  # :378-385
+        ehs = emb.unsqueeze(1)
+        if do_cfg:
+            ehs = torch.cat([torch.zeros_like(ehs), ehs], dim=0)
+        mark("clip")
+
+        latents = inp["latents"].to(dtype).clone()
+        F_, h, w = latents.shape[2], latents.shape[3], latents.shape[4]
+        enc, _ = self._vae()
+        ref_latents = enc.encode_mean(inp["ref"]) * 0.18215  # :424-431
+        bk_lat = (enc.encode_mean(inp["bk_unique"]) * 0.18215)[inp["bk_inverse"].to(device)]
+        vid_bk = bk_lat.permute(1, 0, 2, 3).unsqueeze(0).to(dtype).contiguous()  # [1, 4, F, h, w]  :434-443
+        mark("vae_encode")
+
+        pose_fea = self.pose_guider.forward_nhwc(inp["pose"]).reshape(F_, h * w, -1)  # channels-last, per frame
+        mark("pose_guider")
+
+        # reference UNet once, banks -> denoising engine (pipeline :393-406, :480-490)
+        writer = ReferenceAttentionControl(self.reference_unet, do_classifier_free_guidance=do_cfg, mode="write",
+                                           batch_size=1, fusion_blocks="full")
+        reader = ReferenceAttentionControl(self.denoising_unet, do_classifier_free_guidance=do_cfg, mode="read",
+                                           batch_size=1, fusion_blocks="full")
+        self.reference_unet(ref_latents.to(dtype).repeat(2 if do_cfg else 1, 1, 1, 1), torch.zeros((), dtype=torch.int64),
+                            encoder_hidden_states=ehs, return_dict=False)
+        reader.update(writer)
+        den = self.denoising_unet.engine()
+        mark("reference_unet")
+
+        context_scheduler = get_context_scheduler(context_schedule)
+        windows = list(context_scheduler(0, num_inference_steps, F_, context_frames, context_stride, context_overlap))
+        rep = 2 if do_cfg else 1
+        single = len(windows) == 1
+        win_inputs = []
+        for c in windows:  # the windows and their pose features are the same at every step (pipeline :493-500)
+            pose_in = pose_fea[c].reshape(1, len(c) * h * w, -1).repeat(rep, 1, 1).reshape(rep * len(c) * h * w, -1)
+            win_inputs.append((c, vid_bk[:, :, c], pose_in.contiguous()))
+        for i, t in enumerate(timesteps):
+            if not single:
+                noise_pred = torch.zeros((rep, 4, F_, h, w), device=device, dtype=dtype)
+                counter = torch.zeros((F_,), device=device, dtype=dtype)
+            for c, bk_c, pose_in in win_inputs:
+                lat_in = torch.cat([latents[:, :, c], bk_c], dim=1).repeat(rep, 1, 1, 1, 1)
+                pred = den.forward(lat_in, t, pose_in)
+                if single:
+                    noise_pred, counter = pred, None
+                else:
+                    noise_pred[:, :, c] = noise_pred[:, :, c] + pred  # :540-542
+                    counter[c] = counter[c] + 1
+            co = self.scheduler.step_coefficients(t)
+            if do_cfg:
+                ops.cfg_ddim_step(noise_pred[0], noise_pred[1], latents, guidance_scale, *co, counter=counter,
+                                  frame_stride=h * w)
+            else:
+                ops.cfg_ddim_step(noise_pred[0], noise_pred[0], latents, 1.0, *co, counter=counter, frame_stride=h * w)
+            if callback is not None and i % callback_steps == 0:
+                callback(i, t, latents)
+        mark("denoise")
+        reader.clear()
+        writer.clear()
+        out = {"latents": latents}
+        if decode:
+            out["videos"] = self.decode_latents_device(latents)
+            mark("vae_decode")
+        self._marks = marks
+        self.last_latents = latents
+        return out
+
+    def _collect_timings(self):
+        m = self._marks
+        self.timings = {m[k][0] + "_ms": m[k - 1][1].elapsed_time(m[k][1]) for k in range(1, len(m))}
+
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, ref_image, pose_images, vid_bk_images, width, height, video_length, num_inference_steps,
+                 guidance_scale, num_images_per_prompt=1, eta: float = 0.0,
+                 generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+                 output_type: Optional[str] = "tensor", return_dict: bool = True,
+                 callback: Optional[Callable[[int, int, torch.Tensor], None]] = None,
+                 callback_steps: Optional[int] = 1, context_schedule="uniform", context_frames=24, context_stride=1,
+                 context_overlap=4, context_batch_size=1, interpolation_factor=1, **kwargs):
+        device = self.device
+        if device.type != "cuda":
+            raise MimoError("Pose2VideoPipeline needs its models on a CUDA (sm_100a) device: no CPU fallback")
+        if eta != 0.0 or context_batch_size != 1 or interpolation_factor not in (0, 1) or num_images_per_prompt != 1:
+            raise NotImplementedError("eta != 0, context_batch_size != 1, interpolation_factor >= 2 and "
+                                      "num_images_per_prompt != 1 are outside the reference's shipped configuration")
+        dtype = self.denoising_unet.dtype
+        host = self.preprocess(ref_image, pose_images, vid_bk_images, width, height, video_length, generator, dtype)
+        dev_in = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        self.io_bytes["h2d"] = sum(v.numel() * v.element_size() for v in host.values())
+        out = self.sample_tensors(dev_in, num_inference_steps, guidance_scale, context_schedule, context_frames,
+                                  context_stride, context_overlap, callback, callback_steps)
+        images = out["videos"].cpu().float().numpy()  # :124-126: one D2H of the finished clip
+        self.io_bytes["d2h"] = out["videos"].numel() * out["videos"].element_size()
+        self._collect_timings()
+        if output_type == "tensor":
+            images = torch.from_numpy(images)
+        if not return_dict:
+            return images
+        return Pose2VideoPipelineOutput(videos=images)

@@ -136,3 +136,41 @@ def pose_guider_schema(conditioning_embedding_channels: int = 320, conditioning_
         k += 2
     s.conv("conv_out", c[-1], conditioning_embedding_channels)
     return s.d
+
+
+def vae_schema(block_out_channels: Sequence[int] = (128, 256, 512, 512), layers_per_block: int = 2,
+               latent_channels: int = 4, in_channels: int = 3, out_channels: int = 3) -> Dict[str, Shape]:
+    """diffusers AutoencoderKL (sd-vae-ft-mse layout) [3P]: the checkpoint the reference loads at run_animate.py:70-73."""
+    s = _S()
+    ch = list(block_out_channels)
+    nb = len(ch)
+    s.conv("encoder.conv_in", in_channels, ch[0])
+    out_c = ch[0]
+    for i in range(nb):
+        in_c, out_c = out_c, ch[i]
+        for j in range(layers_per_block):
+            s.resnet(f"encoder.down_blocks.{i}.resnets.{j}", in_c if j == 0 else out_c, out_c, None)
+        if i < nb - 1:
+            s.conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", out_c, out_c)
+    for side in ("encoder", "decoder"):
+        s.resnet(f"{side}.mid_block.resnets.0", ch[-1], ch[-1], None)
+        a = f"{side}.mid_block.attentions.0"
+        s.norm(a + ".group_norm", ch[-1])
+        s.attn(a, ch[-1], bias=True)
+        s.resnet(f"{side}.mid_block.resnets.1", ch[-1], ch[-1], None)
+    s.norm("encoder.conv_norm_out", ch[-1])
+    s.conv("encoder.conv_out", ch[-1], 2 * latent_channels)
+    s.conv("quant_conv", 2 * latent_channels, 2 * latent_channels, k=1)
+    s.conv("post_quant_conv", latent_channels, latent_channels, k=1)
+    rev = ch[::-1]
+    s.conv("decoder.conv_in", latent_channels, rev[0])
+    out_c = rev[0]
+    for i in range(nb):
+        in_c, out_c = out_c, rev[i]
+        for j in range(layers_per_block + 1):
+            s.resnet(f"decoder.up_blocks.{i}.resnets.{j}", in_c if j == 0 else out_c, out_c, None)
+        if i < nb - 1:
+            s.conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", out_c, out_c)
+    s.norm("decoder.conv_norm_out", rev[-1])
+    s.conv("decoder.conv_out", rev[-1], out_channels)
+    return s.d

@@ -90,6 +90,7 @@ SYMBOLS = {
     "mimo_version": (C.c_char_p, []),
     "mimo_last_error": (C.c_char_p, []),
     "mimo_device_check": (C.c_int, [C.c_int]),
+    "mimo_abi_sizeof": (C.c_int, [C.c_int]),
     "mimo_gemm": (C.c_int, [C.POINTER(GemmParams), _VP]),
     "mimo_gemm_geglu_granule": (C.c_int, [_I32]),
     "mimo_conv3x3": (C.c_int, [C.POINTER(Conv3x3Params), _VP]),
@@ -127,6 +128,10 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
         fn.restype = res
         fn.argtypes = args
+    for which, st in enumerate((Epilogue, GemmParams, Conv3x3Params, GroupNormParams, AttnParams)):
+        if lib.mimo_abi_sizeof(which) != C.sizeof(st):
+            raise MimoError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes in lib.py but "
+                            f"{lib.mimo_abi_sizeof(which)} in {LIB_PATH.name}; rebuild the library")
     _lib = lib
     return lib
 

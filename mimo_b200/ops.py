@@ -2,26 +2,49 @@
 every function enqueues exactly the kernels of one C entry point on torch's current CUDA stream.
 
 Activations are channels-last 2-D views: [rows, C] with rows = (frame-sample, y, x).
+
+Optional profiling (bench.py): when PROFILE is a list, every call is bracketed by CUDA events on the launching
+stream and appends (name, flops, bytes, ev_start, ev_stop) with the call's ALGORITHMIC flops / bytes.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import List, Optional
 
 import torch
 
 from . import lib as L
 
-_launches = 0  # number of C-ABI compute calls issued (bench.py's gpu_launches evidence)
+_launches = 0  # number of kernels launched through the C ABI (bench.py's gpu_launches)
+PROFILE: Optional[List[tuple]] = None
 
 
 def launches() -> int:
     return _launches
 
 
-def _count(k: int = 1) -> None:
-    global _launches
-    _launches += k
+class _Call:
+    """Counts kernel launches and, when profiling, brackets the call with events."""
+
+    __slots__ = ("name", "k", "flops", "bytes", "e0")
+
+    def __init__(self, name: str, kernels: int = 1, flops: float = 0.0, bytes_: float = 0.0):
+        self.name, self.k, self.flops, self.bytes = name, kernels, flops, bytes_
+
+    def __enter__(self):
+        global _launches
+        _launches += self.k
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1))
+        return False
 
 
 def _stream() -> C.c_void_p:
@@ -77,8 +100,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *
     p.M, p.N, p.K = M, N, K
     p.dtype = _dt(a)
     p.ep = _epilogue(bias, rowvec, rows_per_group, residual, scale, act)
-    L.check(L.load().mimo_gemm(C.byref(p), _stream()), "mimo_gemm")
-    _count()
+    kt = K + K1
+    with _Call("gemm", 1, 2.0 * M * N * kt, 2.0 * (M * kt + N * kt + M * n_out + (M * N if residual is not None else 0))):
+        L.check(L.load().mimo_gemm(C.byref(p), _stream()), "mimo_gemm")
     return out
 
 
@@ -101,8 +125,10 @@ def conv3x3(x0: torch.Tensor, w: torch.Tensor, n: int, h: int, wd: int, out: Opt
     p.n, p.h, p.w_, p.cout = n, h, wd, cout
     p.dtype = _dt(x0)
     p.ep = _epilogue(bias, rowvec, rows_per_group or h * wd, residual, scale, act)
-    L.check(L.load().mimo_conv3x3(C.byref(p), _stream()), "mimo_conv3x3")
-    _count()
+    M, cin = n * h * wd, c0 + c1
+    with _Call("conv3x3", 1, 2.0 * M * cout * 9 * cin,
+               2.0 * (M * cin + 9 * cin * cout + M * cout + (M * cout if residual is not None else 0))):
+        L.check(L.load().mimo_conv3x3(C.byref(p), _stream()), "mimo_conv3x3")
     return out
 
 
@@ -114,9 +140,9 @@ def im2col3x3(x: torch.Tensor, n: int, h: int, wd: int, *, stride=1, upshift=0, 
     ow = (uw + 2 * pad_lo - 3 + (0 if pad_lo else 1)) // stride + 1
     if out is None:
         out = torch.empty((n * oh * ow, 9 * c), dtype=x.dtype, device=x.device)
-    L.check(L.load().mimo_im2col3x3(_ptr(x), _ptr(out), n, h, wd, c, stride, upshift, pad_lo, out.stride(0),
-                                    _dt(x), _stream()), "mimo_im2col3x3")
-    _count()
+    with _Call("im2col", 1, 0.0, 2.0 * (x.numel() + out.numel())):
+        L.check(L.load().mimo_im2col3x3(_ptr(x), _ptr(out), n, h, wd, c, stride, upshift, pad_lo, out.stride(0),
+                                        _dt(x), _stream()), "mimo_im2col3x3")
     return out
 
 
@@ -140,8 +166,8 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int,
     p.eps = float(eps)
     p.silu = int(bool(silu))
     p.dtype = _dt(x0)
-    L.check(L.load().mimo_groupnorm(C.byref(p), _stream()), "mimo_groupnorm")
-    _count(2)
+    with _Call("groupnorm", 2, 0.0, 2.0 * 2 * out.numel()):  # algorithmic: one read + one write
+        L.check(L.load().mimo_groupnorm(C.byref(p), _stream()), "mimo_groupnorm")
     return out
 
 
@@ -150,17 +176,18 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps=1
     assert x.is_contiguous() and x.dim() == 2
     if out is None:
         out = torch.empty_like(x)
-    L.check(L.load().mimo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), x.shape[0], x.shape[1], float(eps),
-                                    _ptr(pe), int(rows_per_frame), int(frames), _dt(x), _stream()), "mimo_layernorm")
-    _count()
+    with _Call("layernorm", 1, 0.0, 2.0 * 2 * x.numel()):
+        L.check(L.load().mimo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), x.shape[0], x.shape[1], float(eps),
+                                        _ptr(pe), int(rows_per_frame), int(frames), _dt(x), _stream()), "mimo_layernorm")
     return out
 
 
 def attn_spatial(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n: int, lq: int, heads: int, *,
                  bank_k: Optional[torch.Tensor] = None, bank_v: Optional[torch.Tensor] = None,
                  bank_index: Optional[torch.Tensor] = None, scale: Optional[float] = None,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q/k/v: [n*lq, C] column slices (views) of one fused buffer; bank_k/v: [nb*lb, C]; bank_index int32 [n]."""
+                 out: Optional[torch.Tensor] = None, n_bank_frames: Optional[int] = None) -> torch.Tensor:
+    """q/k/v: [n*lq, C] column slices (views) of one fused buffer; bank_k/v: [nb, lb, C]; bank_index int32 [n].
+    n_bank_frames (profiling only): how many of the n frames attend to the bank."""
     Cdim = q.shape[1]
     d = Cdim // heads
     assert q.stride(0) == k.stride(0) == v.stride(0) and q.stride(1) == 1
@@ -168,12 +195,14 @@ def attn_spatial(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n: int, lq: 
         out = torch.empty((n * lq, Cdim), dtype=q.dtype, device=q.device)
     p = L.AttnParams()
     p.q, p.k, p.v, p.ld_qkv = _ptr(q), _ptr(k), _ptr(v), q.stride(0)
+    lb = 0
     if bank_k is not None:
         assert bank_v is not None and bank_index is not None and bank_index.dtype == torch.int32
         assert bank_k.stride(0) == bank_v.stride(0)
         nb = 1 if bank_k.dim() == 2 else bank_k.shape[0]
         p.bank_k, p.bank_v, p.ld_bank = _ptr(bank_k), _ptr(bank_v), bank_k.stride(-2)
-        p.lb = bank_k.shape[-2]
+        lb = bank_k.shape[-2]
+        p.lb = lb
         p.nb = nb
         p.bank_index = _ptr(bank_index)
     else:
@@ -183,8 +212,9 @@ def attn_spatial(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n: int, lq: 
     p.n, p.lq, p.heads, p.d = n, lq, heads, d
     p.scale = float(scale if scale is not None else d ** -0.5)
     p.dtype = _dt(q)
-    L.check(L.load().mimo_attn_spatial(C.byref(p), _stream()), "mimo_attn_spatial")
-    _count()
+    nbf = (n if n_bank_frames is None else n_bank_frames) if lb else 0
+    with _Call("attn_spatial", 1, 4.0 * Cdim * lq * (n * lq + nbf * lb), 2.0 * (4 * n * lq * Cdim + 2 * lb * Cdim)):
+        L.check(L.load().mimo_attn_spatial(C.byref(p), _stream()), "mimo_attn_spatial")
     return out
 
 
@@ -194,10 +224,11 @@ def attn_temporal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int,
     d = Cdim // heads
     if out is None:
         out = torch.empty((batch * frames * hw, Cdim), dtype=q.dtype, device=q.device)
-    L.check(L.load().mimo_attn_temporal(_ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0), batch, frames,
-                                        hw, heads, d, float(scale if scale is not None else d ** -0.5), _dt(q),
-                                        _stream()), "mimo_attn_temporal")
-    _count()
+    rows = batch * frames * hw
+    with _Call("attn_temporal", 1, 4.0 * rows * frames * Cdim, 2.0 * 4 * rows * Cdim):
+        L.check(L.load().mimo_attn_temporal(_ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0), batch,
+                                            frames, hw, heads, d, float(scale if scale is not None else d ** -0.5),
+                                            _dt(q), _stream()), "mimo_attn_temporal")
     return out
 
 
@@ -206,9 +237,9 @@ def ncfhw_to_nhwc(src: torch.Tensor, cpad: int, dtype: torch.dtype, out: Optiona
     assert src.is_contiguous() and src.dtype in (torch.float32, dtype)
     if out is None:
         out = torch.empty((b * f * h * w, cpad), dtype=dtype, device=src.device)
-    L.check(L.load().mimo_ncfhw_to_nhwc(_ptr(src), _ptr(out), b, c, f, h, w, cpad, int(src.dtype == torch.float32),
-                                        _dt(out), _stream()), "mimo_ncfhw_to_nhwc")
-    _count()
+    with _Call("layout", 1, 0.0, src.numel() * src.element_size() + 2.0 * out.numel()):
+        L.check(L.load().mimo_ncfhw_to_nhwc(_ptr(src), _ptr(out), b, c, f, h, w, cpad,
+                                            int(src.dtype == torch.float32), _dt(out), _stream()), "mimo_ncfhw_to_nhwc")
     return out
 
 
@@ -217,9 +248,9 @@ def nhwc_to_ncfhw(src: torch.Tensor, b: int, c: int, f: int, h: int, w: int, *, 
     out_dtype = out_dtype or src.dtype
     if out is None:
         out = torch.empty((b, c, f, h, w), dtype=out_dtype, device=src.device)
-    L.check(L.load().mimo_nhwc_to_ncfhw(_ptr(src), _ptr(out), b, c, f, h, w, src.stride(0),
-                                        int(out.dtype == torch.float32), _dt(src), _stream()), "mimo_nhwc_to_ncfhw")
-    _count()
+    with _Call("layout", 1, 0.0, 2.0 * b * c * f * h * w + out.numel() * out.element_size()):
+        L.check(L.load().mimo_nhwc_to_ncfhw(_ptr(src), _ptr(out), b, c, f, h, w, src.stride(0),
+                                            int(out.dtype == torch.float32), _dt(src), _stream()), "mimo_nhwc_to_ncfhw")
     return out
 
 
@@ -228,31 +259,32 @@ def upsample2x(x: torch.Tensor, n: int, h: int, w: int, out: Optional[torch.Tens
     assert x.is_contiguous()
     if out is None:
         out = torch.empty((n * 4 * h * w, c), dtype=x.dtype, device=x.device)
-    L.check(L.load().mimo_upsample2x(_ptr(x), _ptr(out), n, h, w, c, _dt(x), _stream()), "mimo_upsample2x")
-    _count()
+    with _Call("upsample2x", 1, 0.0, 2.0 * 5 * x.numel()):
+        L.check(L.load().mimo_upsample2x(_ptr(x), _ptr(out), n, h, w, c, _dt(x), _stream()), "mimo_upsample2x")
     return out
 
 
 def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
     assert x.dim() == 2 and x.stride(1) == 1
-    L.check(L.load().mimo_softmax_rows(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _dt(x), _stream()), "mimo_softmax_rows")
-    _count()
+    with _Call("softmax_rows", 1, 0.0, 2.0 * 2 * x.numel()):
+        L.check(L.load().mimo_softmax_rows(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _dt(x), _stream()),
+                "mimo_softmax_rows")
     return x
 
 
 def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if out is None:
         out = torch.empty_like(a)
-    L.check(L.load().mimo_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), _dt(a), _stream()), "mimo_add")
-    _count()
+    with _Call("elementwise", 1, 0.0, 2.0 * 3 * a.numel()):
+        L.check(L.load().mimo_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), _dt(a), _stream()), "mimo_add")
     return out
 
 
 def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if out is None:
         out = torch.empty_like(x)
-    L.check(L.load().mimo_silu(_ptr(x), _ptr(out), x.numel(), _dt(x), _stream()), "mimo_silu")
-    _count()
+    with _Call("elementwise", 1, 0.0, 2.0 * 2 * x.numel()):
+        L.check(L.load().mimo_silu(_ptr(x), _ptr(out), x.numel(), _dt(x), _stream()), "mimo_silu")
     return out
 
 
@@ -260,11 +292,12 @@ def cfg_ddim_step(pred_uncond: torch.Tensor, pred_cond: torch.Tensor, latents: t
                   sqrt_a_t: float, sqrt_1ma_t: float, sqrt_a_prev: float, sqrt_1ma_prev: float, *,
                   counter: Optional[torch.Tensor] = None, frame_stride: int = 0) -> torch.Tensor:
     """In-place DDIM update of `latents` from the two CFG halves of the (window-accumulated) prediction."""
-    L.check(L.load().mimo_cfg_ddim_step(_ptr(pred_uncond), _ptr(pred_cond), _ptr(counter), int(frame_stride),
-                                        _ptr(latents), latents.numel(), float(guidance), float(sqrt_a_t),
-                                        float(sqrt_1ma_t), float(sqrt_a_prev), float(sqrt_1ma_prev), _dt(latents),
-                                        _stream()), "mimo_cfg_ddim_step")
-    _count()
+    assert pred_uncond.is_contiguous() and pred_cond.is_contiguous() and latents.is_contiguous()
+    with _Call("cfg_ddim", 1, 0.0, 2.0 * 4 * latents.numel()):
+        L.check(L.load().mimo_cfg_ddim_step(_ptr(pred_uncond), _ptr(pred_cond), _ptr(counter), int(frame_stride),
+                                            _ptr(latents), latents.numel(), float(guidance), float(sqrt_a_t),
+                                            float(sqrt_1ma_t), float(sqrt_a_prev), float(sqrt_1ma_prev), _dt(latents),
+                                            _stream()), "mimo_cfg_ddim_step")
     return latents
 
 

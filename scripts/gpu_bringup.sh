@@ -6,7 +6,7 @@ LOG=gpurun_out/bringup.log
 : > $LOG
 for t in ${@:-gemm_basic gemm_shapes gemm_persistent gemm_epilogue conv_basic conv_shapes norms temporal elementwise spatial_basic spatial_shapes perf}; do
   echo "##### $t" >> $LOG
-  timeout 240 python tools/gpu_probe.py $t >> $LOG 2>&1
+  timeout 240 python scripts/gpu_probe.py $t >> $LOG 2>&1
   echo "exit=$?" >> $LOG
 done
 grep -E "^\[|^==|exit=|#####|TFLOP|GB/s" $LOG | tail -150

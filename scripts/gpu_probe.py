@@ -1,8 +1,8 @@
 """Kernel bring-up probe (GPU box only): runs one named check against a plain PyTorch fp32 reference and prints
 compact diagnostics. Each check is meant to run in its own process (a trapped kernel poisons the context):
 
-    python tools/gpu_probe.py list
-    python tools/gpu_probe.py <name> [...]
+    python scripts/gpu_probe.py list
+    python scripts/gpu_probe.py <name> [...]
 """
 from __future__ import annotations
 

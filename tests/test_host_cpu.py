@@ -1,0 +1,87 @@
+"""Host-side logic of the drop-in surface (no GPU): state-dict schema, context windows, scheduler tables,
+constructor validation — each against the oracle / the reference-generated golden tables."""
+import json
+
+import pytest
+import torch
+
+from mimo_b200.host import context, schema
+from mimo_b200.host.scheduler import DDIMScheduler
+from oracle import torch_oracle as O
+
+SCHED_KW = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, steps_offset=1,
+                prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")
+
+
+def _same(sch, sd, name):
+    assert set(sch) == set(sd), (name, sorted(set(sch) ^ set(sd))[:8])
+    for k, shp in sch.items():
+        assert tuple(shp) == tuple(sd[k].shape), (name, k)
+
+
+def test_state_dict_schema_matches_reference_layout():
+    cfg = O.UNetConfig(block_out_channels=(64, 128, 256, 256))
+    w = cfg.block_out_channels
+    _same(schema.unet_schema(w), O.make_denoising_unet_sd(cfg), "denoising unet")
+    _same(schema.unet_schema(w, in_channels=4, motion=False, out_head=False), O.make_reference_unet_sd(cfg), "reference unet")
+    _same(schema.pose_guider_schema(320), O.make_pose_guider_sd(), "pose guider")
+    vcfg = O.VAEConfig(block_out_channels=(32, 64, 128, 128))
+    _same(schema.vae_schema(vcfg.block_out_channels), O.make_vae_sd(vcfg), "vae")
+    # full-size parameter counts quoted by SURVEY.md (1 312.7 M / 859.5 M / 1.09 M)
+    n = lambda s: sum(int(torch.tensor(v).prod()) for k, v in s.items() if not k.endswith(".pe"))
+    assert abs(n(schema.unet_schema()) / 1e6 - 1312.7) < 0.5
+    assert abs(n(schema.unet_schema(in_channels=4, motion=False, out_head=False)) / 1e6 - 859.5) < 0.5
+    assert abs(n(schema.pose_guider_schema(320)) / 1e6 - 1.09) < 0.02
+
+
+def test_facade_modules_round_trip_state_dict():
+    from mimo_b200.host.modules import PoseGuider, UNet2DConditionModel
+    cfg = O.UNetConfig(block_out_channels=(32, 64, 64, 64))
+    sd = O.make_reference_unet_sd(cfg)
+    m = UNet2DConditionModel(block_out_channels=cfg.block_out_channels, cross_attention_dim=768, attention_head_dim=8)
+    m.load_state_dict(sd, strict=True)
+    back = m.state_dict()
+    assert list(back) != [] and all(torch.equal(back[k], sd[k]) for k in sd)
+    assert m.half().dtype == torch.float16
+    pg = PoseGuider(320, 3, (16, 32, 96, 256))
+    pg.load_state_dict(O.make_pose_guider_sd(), strict=True)
+    with pytest.raises(RuntimeError):
+        pg.load_state_dict({"conv_in.weight": torch.zeros(1)}, strict=True)
+
+
+def test_context_windows_match_reference(golden_dir):
+    tables = json.loads((golden_dir / "integer_tables.json").read_text())
+    for F, want in tables["windows"].items():
+        assert list(context.uniform(0, 20, int(F), 24, 1, 4)) == want
+    with pytest.raises(ValueError):
+        context.get_context_scheduler("nope")
+    for v in (0, 1, 2, 3, 12345, 2 ** 63):
+        assert context.ordered_halving(v) == O.ordered_halving(v)
+
+
+def test_scheduler_tables_match_reference(golden_dir):
+    tables = json.loads((golden_dir / "integer_tables.json").read_text())
+    for N, want in tables["timesteps"].items():
+        s = DDIMScheduler(**SCHED_KW)
+        s.set_timesteps(int(N))
+        assert [int(t) for t in s.timesteps] == want
+        d = O.DDIM()
+        d.set_timesteps(int(N))
+        for t in want:
+            assert s.step_coefficients(t) == d.coefficients(t)
+    with pytest.raises(NotImplementedError):
+        DDIMScheduler(clip_sample=True)
+
+
+def test_unsupported_configurations_fail_loudly():
+    from mimo_b200.host.modules import ReferenceAttentionControl, UNet3DConditionModel
+    with pytest.raises(NotImplementedError):
+        UNet3DConditionModel(block_out_channels=(32, 64, 64, 64), use_motion_module=False)
+    kw = dict(use_motion_module=True, motion_module_mid_block=True, motion_module_type="Vanilla",
+              motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1,
+                                        attention_block_types=["Temporal_Self", "Temporal_Self"],
+                                        temporal_position_encoding=True, temporal_position_encoding_max_len=32))
+    m = UNet3DConditionModel(block_out_channels=(32, 64, 64, 64), cross_attention_dim=768, **kw)
+    assert m.state_dict()["conv_in.weight"].shape[1] == 8  # forced 8 input channels
+    with pytest.raises(NotImplementedError):
+        ReferenceAttentionControl(m, mode="read", fusion_blocks="midup")
