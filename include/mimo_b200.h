@@ -41,7 +41,7 @@ const char* mimo_last_error(void);
 /* 0 if device `dev` is sm_100; MIMO_ERR_DEVICE otherwise (also when there is no CUDA device at all). */
 int mimo_device_check(int dev);
 /* sizeof() of the parameter structs as compiled into the library (0 epilogue, 1 gemm, 2 conv3x3, 3 groupnorm,
- * 4 attn): lets a binding verify its struct mirrors before the first call. */
+ * 4 attn, 5 attn_temporal): lets a binding verify its struct mirrors before the first call. */
 int mimo_abi_sizeof(int which);
 
 /* Fused epilogue shared by GEMM and conv:  out = act((acc + bias[c] + rowvec[row / rows_per_group][c]
@@ -129,12 +129,13 @@ typedef struct {
 int mimo_groupnorm(const mimo_groupnorm_params* p, void* stream);
 
 /* LayerNorm over the last dim; optional additive per-frame vector AFTER the affine (the motion module's
- * sinusoidal positional encoding): out[r] = LN(x[r]) * gamma + beta + pe[(r / rows_per_frame) % frames].
+ * sinusoidal positional encoding): out[r] = LN(x[r]) * gamma + beta + pe[pe_frame_offset + (r / rows_per_frame) % frames]
+ * (pe_frame_offset = first global frame of this rank's shard).
  * Replaces nn.LayerNorm (src/models/attention.py:329-360; motion_module.py:230,236) and PositionalEncoding.forward
  * (motion_module.py:277-279). */
 int mimo_layernorm(const void* x, const void* gamma, const void* beta, void* out, int64_t rows, int32_t c,
-                   float eps, const void* pe, int64_t rows_per_frame, int32_t frames, int32_t dtype,
-                   void* stream);
+                   float eps, const void* pe, int64_t rows_per_frame, int32_t frames, int32_t pe_frame_offset,
+                   int32_t dtype, void* stream);
 
 /* Spatial self-attention with the reference-image bank (flash attention, tcgen05 QK^T and PV, online softmax).
  * q/k/v: [n, lq, heads, d] slices of a fused QKV buffer (row stride ld_qkv elements). bank_k/bank_v:
@@ -161,12 +162,28 @@ typedef struct {
 } mimo_attn_params;
 int mimo_attn_spatial(const mimo_attn_params* p, void* stream);
 
-/* Temporal self-attention of the motion module: for every (batch b, pixel p, head) a frames x frames attention.
- * qkv rows are ordered ((b * frames + f) * hw + p); q/k/v are column slices. Replaces VersatileAttention.forward
- * (src/models/motion_module.py:353-390), including its two "(b f) d c <-> (b d) f c" transposes. */
-int mimo_attn_temporal(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out,
-                       int32_t batch, int32_t frames, int32_t hw, int32_t heads, int32_t d, float scale,
-                       int32_t dtype, void* stream);
+/* Temporal self-attention of the motion module: for every (batch b, pixel p, head) a q_frames x kv_frames attention
+ * over the frame axis. Query rows are ordered ((b * q_frames + f) * hw + p). Keys/values cover all kv_frames frames
+ * and may live in several chunks of frames_per_chunk frames (the per-rank buffers of a frame-sharded clip after the
+ * all-gather): kv_row(b, f, p) = (f / frames_per_chunk) * chunk_stride_rows + (b * frames_per_chunk + f %
+ * frames_per_chunk) * hw + p. Single GPU: q_frames == kv_frames == frames_per_chunk, chunk_stride_rows = 0.
+ * Replaces VersatileAttention.forward (src/models/motion_module.py:353-390), including its two
+ * "(b f) d c <-> (b d) f c" transposes. */
+typedef struct {
+  const void* q;
+  int64_t ld_q;
+  const void* k;
+  const void* v;
+  int64_t ld_kv;
+  void* out;
+  int64_t ld_out;
+  int64_t chunk_stride_rows;
+  int32_t batch, q_frames, kv_frames, frames_per_chunk;
+  int32_t hw, heads, d;
+  float scale;
+  int32_t dtype;
+} mimo_attn_temporal_params;
+int mimo_attn_temporal(const mimo_attn_temporal_params* p, void* stream);
 
 /* Elementwise / layout helpers (each one coalesced pass). */
 /* [b, c, f, h, w] (reference layout) -> [(b f), h, w, cpad] channels-last, zero-padding channels c..cpad */

@@ -1,0 +1,26 @@
+// Shared declarations of the spatial-attention kernels (attn_spatial.cu: one Q tile per CTA, any head dim up to 192;
+// attn_spatial_pp.cu: two Q tiles per CTA in ping-pong, head dim <= 64).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace mimo {
+
+constexpr int BQ = 128;                 // query rows per tile
+constexpr int BKV = 128;                // keys per tile
+constexpr int kChunkBytes = 128 * 128;  // one 64-element-wide (128 B) chunk of a 128-row tile
+
+struct AttnArgs {
+  int lq, lb, heads, d, dp;  // dp = d rounded up to 16
+  int n_self_tiles, n_bank_tiles;
+  float scale_log2;
+  const int* bank_index;
+  void* out;
+  long long ld_out;
+};
+
+// two Q tiles per CTA (grid.x = ceil(lq / 256)); dp <= 64
+int launch_attn_pp(bool bf16, const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& bk,
+                   const CUtensorMap& bv, const AttnArgs& a, int n, cudaStream_t st);
+
+}  // namespace mimo

@@ -15,24 +15,14 @@
 #include <cuda_runtime.h>
 
 #include "../../include/mimo_b200.h"
+#include "attn_common.h"
 #include "host_util.h"
 #include "ptx.cuh"
 
 namespace mimo {
 
 constexpr int kAttnThreads = 256;
-constexpr int BQ = 128;   // query rows per CTA
-constexpr int BKV = 128;  // keys per tile
-constexpr int kChunkBytes = 128 * 128;  // one 64-element-wide chunk of a 128-row tile
-
-struct AttnArgs {
-  int lq, lb, heads, d, dp;  // dp = d rounded up to 16
-  int n_self_tiles, n_bank_tiles;
-  float scale_log2;
-  const int* bank_index;
-  void* out;
-  long long ld_out;
-};
+static int g_attn_variant = 0;  // test hook: 0 = auto, 1 = force the single-tile kernel
 
 template <int NCH, int KVST>
 struct AttnCfg {
@@ -310,6 +300,11 @@ static int attn_tmap(CUtensorMap* m, int dtype, const void* base, int d, int hea
 
 using namespace mimo;
 
+extern "C" int mimo_debug_attn_variant(int v) {
+  g_attn_variant = v;
+  return 0;
+}
+
 extern "C" int mimo_attn_spatial(const mimo_attn_params* p, void* stream) {
   if (!p || !p->q || !p->k || !p->v || !p->out) return set_error(MIMO_ERR_ARG, "mimo_attn_spatial: null pointer");
   if (p->n <= 0 || p->lq <= 0 || p->heads <= 0 || p->d <= 0 || (p->d % 8) || p->d > 192 || (p->ld_qkv % 8) ||
@@ -348,6 +343,7 @@ extern "C" int mimo_attn_spatial(const mimo_attn_params* p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nch = (a.dp + 63) / 64;
   const bool bf = p->dtype == MIMO_BF16;
+  if (nch == 1 && g_attn_variant != 1) return launch_attn_pp(bf, tq, tk, tv, tbk, tbv, a, p->n, st);
   if (nch == 1) return bf ? launch_attn<1, 2, true>(tq, tk, tv, tbk, tbv, a, grid, st)
                           : launch_attn<1, 2, false>(tq, tk, tv, tbk, tbv, a, grid, st);
   if (nch == 2) return bf ? launch_attn<2, 2, true>(tq, tk, tv, tbk, tbv, a, grid, st)

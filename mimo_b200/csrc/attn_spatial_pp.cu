@@ -1,0 +1,328 @@
+// Spatial self-attention with the reference bank, head dim <= 64 (the UNet's 64x64 level: d = 40, 87 % of all
+// attention FLOPs): flash attention with TWO 128-row query tiles per CTA processed in ping-pong.
+//
+//   warp 0 lane 0 : TMA      - Q tiles A and B once; K/V tiles in a 2-stage ring shared by both query tiles
+//   warp 1 lane 0 : MMA      - S_X = Q_X K^T (128x128xdp) and O_X += P_X V (128xdpx128), X in {A, B}, interleaved so
+//                              the tensor pipe works on one query tile while the other one is in its softmax
+//   warp 2        : TMEM allocator (512 columns: S_A, S_B, O_A, O_B)
+//   warps 4-7     : softmax warpgroup A (one thread per query row = TMEM lane)
+//   warps 8-11    : softmax warpgroup B
+// Softmax: base-2 exponentials (ex2.approx), fp32 running sum, LAZY rescaling — the reference maximum of a row is only
+// moved (and O rescaled in TMEM) when the tile maximum exceeds it by more than 2^8, which keeps P within fp16
+// range and is exact after the final division by the row sum. P goes to shared memory as the 128B-swizzled K-major A
+// operand of the P.V MMA; V tiles are used in place as MN-major B operands.
+#include <cuda_runtime.h>
+
+#include "../../include/mimo_b200.h"
+#include "attn_common.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace mimo {
+
+constexpr int kPPThreads = 384;
+constexpr int kPPQBytes = 2 * kChunkBytes;        // Q_A, Q_B
+constexpr int kPPKVStage = 2 * kChunkBytes;       // K then V
+constexpr int kPPPBytes = 2 * 2 * kChunkBytes;    // P_A, P_B (two 64-key chunks each)
+constexpr int kPPSmem = kPPQBytes + 2 * kPPKVStage + kPPPBytes + 256;
+constexpr float kRescaleThreshold = 8.0f;         // log2 units
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kPPThreads, 1)
+attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
+                       const __grid_constant__ CUtensorMap tmBV, AttnArgs a) {
+  using C = Cvt<kBf16>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + kPPQBytes;
+  uint8_t* sP = sKV + 2 * kPPKVStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPPPBytes);
+  uint64_t* q_full = bars;           // 1
+  uint64_t* kv_full = bars + 1;      // 2
+  uint64_t* kv_empty = bars + 3;     // 2
+  uint64_t* s_full = bars + 5;       // 2 (per query tile)
+  uint64_t* p_full = bars + 7;       // 2
+  uint64_t* o_done = bars + 9;       // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_pair = blockIdx.x;
+  const int h = blockIdx.y;
+  const int n = blockIdx.z;
+  const int bidx = a.bank_index ? a.bank_index[n] : -1;
+  const int T = a.n_self_tiles + (bidx >= 0 ? a.n_bank_tiles : 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    if (bidx >= 0) {
+      tma_prefetch_desc(&tmBK);
+      tma_prefetch_desc(&tmBV);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&o_done[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_expect_tx(q_full, kPPQBytes);
+    tma_load_4d(sQ, &tmQ, q_full, 0, h, q_pair * 2 * BQ, n);
+    tma_load_4d(sQ + kChunkBytes, &tmQ, q_full, 0, h, q_pair * 2 * BQ + BQ, n);
+    for (int j = 0; j < T; ++j) {
+      const int stage = j & 1;
+      mbar_wait(&kv_empty[stage], ((j >> 1) & 1u) ^ 1u);
+      uint8_t* sk = sKV + stage * kPPKVStage;
+      mbar_expect_tx(&kv_full[stage], kPPKVStage);
+      const bool bank = j >= a.n_self_tiles;
+      const int row0 = (bank ? j - a.n_self_tiles : j) * BKV;
+      const int img = bank ? bidx : n;
+      tma_load_4d(sk, bank ? &tmBK : &tmK, &kv_full[stage], 0, h, row0, img);
+      tma_load_4d(sk + kChunkBytes, bank ? &tmBV : &tmV, &kv_full[stage], 0, h, row0, img);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_qk = make_idesc_f16(BQ, BKV, kBf16, false, false);
+    const uint32_t idesc_pv = make_idesc_f16(BQ, a.dp, kBf16, false, true);  // B (= V) is MN-major
+    const int ksteps_qk = a.dp / 16;
+    const uint32_t q_addr = smem_u32(sQ);
+    const uint32_t p_addr = smem_u32(sP);
+    auto issue_qk = [&](int x, int j) {
+      const uint32_t k_addr = smem_u32(sKV + (j & 1) * kPPKVStage);
+      const uint32_t qa = q_addr + x * kChunkBytes;
+      for (int ks = 0; ks < ksteps_qk; ++ks)
+        umma_ss(tmem_base + x * 128, make_smem_desc_sw128(qa + ks * 32, 16, 1024),
+                make_smem_desc_sw128(k_addr + ks * 32, 16, 1024), idesc_qk, ks != 0 ? 1u : 0u);
+      tc_commit(&s_full[x]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    for (int j = 0; j < T; ++j) {
+      const int stage = j & 1;
+      const uint32_t v_addr = smem_u32(sKV + stage * kPPKVStage + kChunkBytes);
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait(&p_full[x], j & 1);
+        tc_fence_after();
+        const uint32_t pa0 = p_addr + x * 2 * kChunkBytes;
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const uint32_t pa = pa0 + (ks >> 2) * kChunkBytes + (ks & 3) * 32;
+          umma_ss(tmem_base + 256 + x * 64, make_smem_desc_sw128(pa, 16, 1024),
+                  make_smem_desc_sw128(v_addr + ks * 2048, kChunkBytes, 1024), idesc_pv, (j | ks) != 0 ? 1u : 0u);
+        }
+        if (x == 1) tc_commit(&kv_empty[stage]);  // both query tiles are done with K[j] and V[j]
+        tc_commit(&o_done[x]);
+        if (j + 1 < T) {
+          if (x == 0) {
+            mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1u);
+            tc_fence_after();
+          }
+          issue_qk(x, j + 1);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax warpgroups =====================
+    const int x = (warp - 4) >> 2;  // query tile A / B
+    const int ew = warp & 3;
+    const int r = ew * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t tS = tmem_base + x * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + x * 64 + lane_off;
+    uint8_t* prow = sP + x * 2 * kChunkBytes + r * 128;
+    const int sw = r & 7;
+    const float sc = a.scale_log2;
+    float m_ref = 0.f, l = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const bool bank = j >= a.n_self_tiles;
+      const int len = bank ? a.lb : a.lq;
+      const int row0 = (bank ? j - a.n_self_tiles : j) * BKV;
+      int valid = len - row0;
+      if (valid > BKV) valid = BKV;
+      mbar_wait(&s_full[x], j & 1);
+      tc_fence_after();
+      // ---- pass 1: tile maximum (4 independent chains) ----
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_x32(tS + hlf * 64, v0);
+        tmem_ld_x32(tS + hlf * 64 + 32, v1);
+        tmem_ld_wait();
+        if (valid == BKV) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(v0[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(v1[i]));
+            mx3 = fmaxf(mx3, __uint_as_float(v1[i + 1]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (hlf * 64 + i < valid) mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
+            if (hlf * 64 + 32 + i < valid) mx1 = fmaxf(mx1, __uint_as_float(v1[i]));
+          }
+        }
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+      // ---- lazy rescale decision ----
+      float alpha = 1.0f;
+      bool rescale = false;
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const bool need = mx > m_ref + kRescaleThreshold;
+        rescale = __any_sync(0xffffffffu, need);
+        if (need) {
+          alpha = fast_exp2(m_ref - mx);
+          m_ref = mx;
+          l *= alpha;
+        }
+      }
+      // P_X (and O_X) may only be overwritten once the previous P_X.V has retired
+      if (j > 0) {
+        mbar_wait(&o_done[x], (j - 1) & 1);
+        tc_fence_after();
+      }
+      // ---- pass 2: probabilities -> swizzled smem ----
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const float nm = -m_ref;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tS + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        if (valid == BKV) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sc, nm));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sc, nm));
+            const float p2 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 2]), sc, nm));
+            const float p3 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 3]), sc, nm));
+            s0 += p0;
+            s1 += p1;
+            s2 += p2;
+            s3 += p3;
+            pk[i] = C::pack(p0, p1);
+            pk[i + 1] = C::pack(p2, p3);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c0 = c * 32 + 2 * i;
+            float p0 = 0.f, p1 = 0.f;
+            if (c0 < valid) p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sc, nm));
+            if (c0 + 1 < valid) p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sc, nm));
+            s0 += p0;
+            s1 += p1;
+            pk[i] = C::pack(p0, p1);
+          }
+        }
+        uint8_t* line = prow + (c >> 1) * kChunkBytes;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int piece = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(line + ((piece ^ sw) << 4)) =
+              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      l += (s0 + s1) + (s2 + s3);
+      // ---- correction of O (rare) ----
+      if (rescale) {
+        for (int c = 0; c < a.dp / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld_x16(tO + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_x16(tO + c * 16, v);
+        }
+        tmem_st_wait();
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[x]);
+    }
+    // ---- epilogue: O / l -> global ----
+    mbar_wait(&o_done[x], (T - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int qrow = q_pair * 2 * BQ + x * BQ + r;
+    typename C::T* orow =
+        static_cast<typename C::T*>(a.out) + (static_cast<long long>(n) * a.lq + qrow) * a.ld_out + h * a.d;
+    for (int c = 0; c < a.dp / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld_x16(tO + c * 16, v);
+      tmem_ld_wait();
+      if (qrow < a.lq) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (c * 16 + q * 8 < a.d) {
+            uint4 o;
+            o.x = C::pack(__uint_as_float(v[q * 8 + 0]) * inv_l, __uint_as_float(v[q * 8 + 1]) * inv_l);
+            o.y = C::pack(__uint_as_float(v[q * 8 + 2]) * inv_l, __uint_as_float(v[q * 8 + 3]) * inv_l);
+            o.z = C::pack(__uint_as_float(v[q * 8 + 4]) * inv_l, __uint_as_float(v[q * 8 + 5]) * inv_l);
+            o.w = C::pack(__uint_as_float(v[q * 8 + 6]) * inv_l, __uint_as_float(v[q * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 16 + q * 8) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_attn_pp(bool bf16, const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& bk,
+                   const CUtensorMap& bv, const AttnArgs& a, int n, cudaStream_t st) {
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[bf16 ? 1 : 0]) {
+    cudaError_t e = bf16 ? cudaFuncSetAttribute(attn_spatial_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPPSmem)
+                         : cudaFuncSetAttribute(attn_spatial_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPPSmem);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_pp)", e);
+    attr_done[bf16 ? 1 : 0] = true;
+  }
+  dim3 grid((a.lq + 2 * BQ - 1) / (2 * BQ), a.heads, n);
+  if (bf16)
+    attn_spatial_pp_kernel<true><<<grid, kPPThreads, kPPSmem, st>>>(q, k, v, bk, bv, a);
+  else
+    attn_spatial_pp_kernel<false><<<grid, kPPThreads, kPPSmem, st>>>(q, k, v, bk, bv, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("attn_pp launch", e);
+  return MIMO_OK;
+}
+
+}  // namespace mimo

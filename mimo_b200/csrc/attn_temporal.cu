@@ -1,11 +1,15 @@
-// Motion-module temporal self-attention: for every (batch b, pixel p, head h) an F x F attention over the
-// frame axis (F <= 32, head dim d in {40, 80, 160, ...} multiple of 8).
+// Motion-module temporal self-attention: for every (batch b, pixel p, head h) an Fq x F attention over the
+// frame axis (F <= 32, head dim d a multiple of 8).
 //
 // One CTA per (b, p): its 8 (= heads) warps stage the K and V rows of all F frames of that pixel in shared
 // memory with 128-bit loads (each row is C contiguous elements), then warp h / lane j computes query row j of
 // head h: scores against the F keys (K rows are smem broadcasts), fp32 softmax, and the PV product 8 output
 // channels at a time. The "(b f) d c <-> (b d) f c" transposes of the reference never materialise: frames are
 // addressed by stride. The op is ~0.2 % of the UNet's FLOPs and HBM/latency bound, hence CUDA cores.
+//
+// Frame sharding: with the clip's frames split over G GPUs the queries are the Fq local frames while K/V cover all
+// F frames, stored as G chunks of frames_per_chunk frames each (the all-gathered per-rank buffers):
+//   kv_row(b, f, p) = (f / fpc) * chunk_stride_rows + (b * fpc + f % fpc) * hw + p
 #include <cuda_runtime.h>
 
 #include "../../include/mimo_b200.h"
@@ -14,35 +18,45 @@
 
 namespace mimo {
 
+struct TemporalArgs {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  long long ld_q, ld_kv, ld_out, chunk_stride_rows;
+  int Fq, F, fpc, hw, heads, d;
+  float scale;
+};
+
 template <bool kBf16>
-__global__ void __launch_bounds__(1024)
-attn_temporal_kernel(const void* __restrict__ qp, const void* __restrict__ kp, const void* __restrict__ vp,
-                     long long ld, void* __restrict__ op, long long ldo, int F, int hw, int heads, int d,
-                     float scale) {
+__global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a) {
   using C = Cvt<kBf16>;
   using T = typename C::T;
   extern __shared__ uint4 smem_kv[];  // K[F][Cdim] then V[F][Cdim], 16-bit
-  const int Cdim = heads * d;
+  const int Cdim = a.heads * a.d;
   const int vecs = Cdim / 8;
   T* sk = reinterpret_cast<T*>(smem_kv);
-  T* sv = sk + static_cast<size_t>(F) * Cdim;
-  const int b = blockIdx.x / hw;
-  const int p = blockIdx.x % hw;
-  const long long tok0 = static_cast<long long>(b) * F * hw + p;  // token of frame 0; frame f adds f * hw
+  T* sv = sk + static_cast<size_t>(a.F) * Cdim;
+  const int b = blockIdx.x / a.hw;
+  const int p = blockIdx.x % a.hw;
 
-  for (int i = threadIdx.x; i < F * vecs; i += blockDim.x) {
+  for (int i = threadIdx.x; i < a.F * vecs; i += blockDim.x) {
     const int f = i / vecs, cv = i % vecs;
-    const long long off = (tok0 + static_cast<long long>(f) * hw) * ld + cv * 8;
-    reinterpret_cast<uint4*>(sk)[i] = *reinterpret_cast<const uint4*>(static_cast<const T*>(kp) + off);
-    reinterpret_cast<uint4*>(sv)[i] = *reinterpret_cast<const uint4*>(static_cast<const T*>(vp) + off);
+    const long long row = static_cast<long long>(f / a.fpc) * a.chunk_stride_rows +
+                          (static_cast<long long>(b) * a.fpc + f % a.fpc) * a.hw + p;
+    const long long off = row * a.ld_kv + cv * 8;
+    reinterpret_cast<uint4*>(sk)[i] = *reinterpret_cast<const uint4*>(static_cast<const T*>(a.k) + off);
+    reinterpret_cast<uint4*>(sv)[i] = *reinterpret_cast<const uint4*>(static_cast<const T*>(a.v) + off);
   }
   __syncthreads();
 
   const int h = threadIdx.x >> 5;
   const int j = threadIdx.x & 31;
-  if (h >= heads || j >= F) return;
+  if (h >= a.heads || j >= a.Fq) return;
+  const int F = a.F, d = a.d;
+  const long long qtok = (static_cast<long long>(b) * a.Fq + j) * a.hw + p;
 
-  const T* qrow = static_cast<const T*>(qp) + (tok0 + static_cast<long long>(j) * hw) * ld + h * d;
+  const T* qrow = static_cast<const T*>(a.q) + qtok * a.ld_q + h * d;
   float s[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) s[i] = 0.f;
@@ -74,7 +88,7 @@ attn_temporal_kernel(const void* __restrict__ qp, const void* __restrict__ kp, c
 #pragma unroll
   for (int i = 0; i < 32; ++i)
     if (i < F) {
-      s[i] *= scale;
+      s[i] *= a.scale;
       m = fmaxf(m, s[i]);
     }
   float sum = 0.f;
@@ -85,7 +99,7 @@ attn_temporal_kernel(const void* __restrict__ qp, const void* __restrict__ kp, c
       sum += s[i];
     }
   const float inv = 1.0f / sum;
-  T* orow = static_cast<T*>(op) + (tok0 + static_cast<long long>(j) * hw) * ldo + h * d;
+  T* orow = static_cast<T*>(a.out) + qtok * a.ld_out + h * d;
   for (int c8 = 0; c8 < d / 8; ++c8) {
     float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -114,28 +128,51 @@ attn_temporal_kernel(const void* __restrict__ qp, const void* __restrict__ kp, c
 
 using namespace mimo;
 
-extern "C" int mimo_attn_temporal(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out,
-                                  int64_t ld_out, int32_t batch, int32_t frames, int32_t hw, int32_t heads,
-                                  int32_t d, float scale, int32_t dtype, void* stream) {
-  if (!q || !k || !v || !out) return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: null pointer");
-  if (batch <= 0 || frames <= 0 || frames > 32 || hw <= 0 || heads <= 0 || heads > 32 || d <= 0 || (d % 8) ||
-      (ld_qkv % 8) || (ld_out % 8))
-    return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: need frames <= 32, heads <= 32, d % 8 == 0");
+extern "C" int mimo_attn_temporal(const mimo_attn_temporal_params* p, void* stream) {
+  if (!p || !p->q || !p->k || !p->v || !p->out) return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: null pointer");
+  const int fpc = p->frames_per_chunk > 0 ? p->frames_per_chunk : p->kv_frames;
+  if (p->batch <= 0 || p->q_frames <= 0 || p->kv_frames <= 0 || p->kv_frames > 32 || p->q_frames > 32 || p->hw <= 0 ||
+      p->heads <= 0 || p->heads > 32 || p->d <= 0 || (p->d % 8) || (p->ld_q % 8) || (p->ld_kv % 8) || (p->ld_out % 8) ||
+      (p->kv_frames % fpc))
+    return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: need frames <= 32, heads <= 32, d % 8 == 0, kv_frames % chunk == 0");
   if (int rc = ensure_device()) return rc;
-  const size_t smem = static_cast<size_t>(2) * frames * heads * d * 2;
+  const size_t smem = static_cast<size_t>(2) * p->kv_frames * p->heads * p->d * 2;
   if (smem > 227 * 1024) return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: K/V tile exceeds shared memory");
+  TemporalArgs a;
+  a.q = p->q;
+  a.k = p->k;
+  a.v = p->v;
+  a.out = p->out;
+  a.ld_q = p->ld_q;
+  a.ld_kv = p->ld_kv;
+  a.ld_out = p->ld_out;
+  a.chunk_stride_rows = p->chunk_stride_rows;
+  a.Fq = p->q_frames;
+  a.F = p->kv_frames;
+  a.fpc = fpc;
+  a.hw = p->hw;
+  a.heads = p->heads;
+  a.d = p->d;
+  a.scale = p->scale;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int threads = heads * 32;
-  const unsigned grid = static_cast<unsigned>(batch) * hw;
+  const int threads = p->heads * 32;
+  const unsigned grid = static_cast<unsigned>(p->batch) * p->hw;
+  static bool attr_done[2] = {false, false};
   cudaError_t e;
-  if (dtype == MIMO_BF16) {
-    e = cudaFuncSetAttribute(attn_temporal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return set_cuda_error("attn_temporal attr", e);
-    attn_temporal_kernel<true><<<grid, threads, smem, st>>>(q, k, v, ld_qkv, out, ld_out, frames, hw, heads, d, scale);
+  if (p->dtype == MIMO_BF16) {
+    if (!attr_done[1]) {
+      e = cudaFuncSetAttribute(attn_temporal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return set_cuda_error("attn_temporal attr", e);
+      attr_done[1] = true;
+    }
+    attn_temporal_kernel<true><<<grid, threads, smem, st>>>(a);
   } else {
-    e = cudaFuncSetAttribute(attn_temporal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return set_cuda_error("attn_temporal attr", e);
-    attn_temporal_kernel<false><<<grid, threads, smem, st>>>(q, k, v, ld_qkv, out, ld_out, frames, hw, heads, d, scale);
+    if (!attr_done[0]) {
+      e = cudaFuncSetAttribute(attn_temporal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return set_cuda_error("attn_temporal attr", e);
+      attr_done[0] = true;
+    }
+    attn_temporal_kernel<false><<<grid, threads, smem, st>>>(a);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("attn_temporal launch", e);

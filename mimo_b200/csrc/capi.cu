@@ -98,6 +98,7 @@ extern "C" int mimo_abi_sizeof(int which) {
     case 2: return static_cast<int>(sizeof(mimo_conv3x3_params));
     case 3: return static_cast<int>(sizeof(mimo_groupnorm_params));
     case 4: return static_cast<int>(sizeof(mimo_attn_params));
+    case 5: return static_cast<int>(sizeof(mimo_attn_temporal_params));
   }
   return -1;
 }

@@ -170,7 +170,7 @@ template <bool kBf16>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ x, const void* __restrict__ gamma, const void* __restrict__ beta,
                  void* __restrict__ out, long long rows, int Cdim, float eps, const void* __restrict__ pe,
-                 long long rows_per_frame, int frames) {
+                 long long rows_per_frame, int frames, int pe_off) {
   using C = Cvt<kBf16>;
   using T = typename C::T;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -214,7 +214,7 @@ layernorm_kernel(const void* __restrict__ x, const void* __restrict__ gamma, con
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / static_cast<float>(Cdim) + eps);
   const T* per = nullptr;
-  if (pe) per = static_cast<const T*>(pe) + ((row / rows_per_frame) % frames) * Cdim;
+  if (pe) per = static_cast<const T*>(pe) + (pe_off + (row / rows_per_frame) % frames) * Cdim;
   T* orow = static_cast<T*>(out) + row * Cdim;
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
@@ -312,7 +312,7 @@ extern "C" int mimo_groupnorm(const mimo_groupnorm_params* p, void* stream) {
 
 extern "C" int mimo_layernorm(const void* x, const void* gamma, const void* beta, void* out, int64_t rows,
                               int32_t c, float eps, const void* pe, int64_t rows_per_frame, int32_t frames,
-                              int32_t dtype, void* stream) {
+                              int32_t pe_frame_offset, int32_t dtype, void* stream) {
   if (!x || !gamma || !beta || !out) return set_error(MIMO_ERR_ARG, "mimo_layernorm: null pointer");
   if (rows <= 0 || c <= 0 || (c % 8) || c > 32 * 8 * kLnMaxVec)
     return set_error(MIMO_ERR_ARG, "mimo_layernorm: c must be a multiple of 8 and <= 2048");
@@ -321,9 +321,9 @@ extern "C" int mimo_layernorm(const void* x, const void* gamma, const void* beta
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned blocks = div_up(rows, 8);
   if (dtype == MIMO_BF16)
-    layernorm_kernel<true><<<blocks, 256, 0, st>>>(x, gamma, beta, out, rows, c, eps, pe, rows_per_frame, frames);
+    layernorm_kernel<true><<<blocks, 256, 0, st>>>(x, gamma, beta, out, rows, c, eps, pe, rows_per_frame, frames, pe_frame_offset);
   else
-    layernorm_kernel<false><<<blocks, 256, 0, st>>>(x, gamma, beta, out, rows, c, eps, pe, rows_per_frame, frames);
+    layernorm_kernel<false><<<blocks, 256, 0, st>>>(x, gamma, beta, out, rows, c, eps, pe, rows_per_frame, frames, pe_frame_offset);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("layernorm launch", e);
   return MIMO_OK;

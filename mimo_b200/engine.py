@@ -242,10 +242,24 @@ class UNetEngine:
         hcur = ops.groupnorm(x, *m["gn"], n, hw, groups=self.spec.motion_groups, eps=1e-6)
         hcur = ops.gemm(hcur, m["pin"][0], bias=m["pin"][1])
         C = hcur.shape[1]
+        rank, world, group = self.shard
         for a in m["attn"]:
-            nh = ops.layernorm(hcur, *a["ln"], pe=a["pe"], rows_per_frame=hw, frames=f)
-            qkv = ops.gemm(nh, a["qkv"])
-            att = ops.attn_temporal(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], b, f, hw, self.spec.heads)
+            if world == 1:
+                nh = ops.layernorm(hcur, *a["ln"], pe=a["pe"], rows_per_frame=hw, frames=f)
+                qkv = ops.gemm(nh, a["qkv"])
+                att = ops.attn_temporal(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], b, f, hw, self.spec.heads)
+            else:
+                # frames are sharded over `world` GPUs: this rank holds frames [rank*f, (rank+1)*f) of the window.
+                # Queries stay local; every rank's K|V block is all-gathered over NVLink (NCCL) and addressed in
+                # place as `world` chunks of f frames (no re-layout copy).
+                import torch.distributed as dist
+                nh = ops.layernorm(hcur, *a["ln"], pe=a["pe"], rows_per_frame=hw, frames=f, pe_frame_offset=rank * f)
+                q = ops.gemm(nh, a["qkv"][:C])
+                kv = ops.gemm(nh, a["qkv"][C:])
+                kv_all = torch.empty((world * kv.shape[0], 2 * C), dtype=kv.dtype, device=kv.device)
+                dist.all_gather_into_tensor(kv_all, kv, group=group)
+                att = ops.attn_temporal(q, kv_all[:, :C], kv_all[:, C:], b, f * world, hw, self.spec.heads, q_frames=f,
+                                        frames_per_chunk=f, chunk_stride_rows=kv.shape[0])
             hcur = ops.gemm(att, a["o"][0], bias=a["o"][1], residual=hcur)
         hcur = self._ff(hcur, m["ffn"], m["geglu"], m["ffo"])
         return ops.gemm(hcur, m["pout"][0], bias=m["pout"][1], residual=x)
@@ -260,6 +274,7 @@ class UNetEngine:
         u = ops.upsample2x(x, n, h, w)
         return ops.conv3x3(u, wp, n, 2 * h, 2 * w, bias=b)
 
+    shard: tuple = (0, 1, None)  # (rank, world, process group) of the frame-sharded execution; world 1 = single GPU
     taps: Optional[dict] = None  # debugging aid (scripts/gpu_probe.py): block outputs as [N, C, H, W] fp32 on CPU
 
     def _tap(self, name, x, n, h, w):

@@ -55,6 +55,14 @@ class Pose2VideoPipeline:
         self.timings: Dict[str, float] = {}
         self.last_latents: Optional[torch.Tensor] = None
         self.io_bytes = {"h2d": 0, "d2h": 0}
+        self._shard = (0, 1, None)  # (rank, world, process group): frame-sharded execution over several GPUs
+
+    def enable_frame_sharding(self, rank: int, world: int, group=None):
+        """Shard every context window's frames over `world` GPUs (one process per GPU, torch.distributed already
+        initialised). Per-frame work is local; the motion modules all-gather K/V over NVLink (engine._motion); the
+        per-window predictions, pose features and decoded frames are all-gathered so that every rank holds the
+        whole clip's latents (they are tiny) and the full result."""
+        self._shard = (rank, world, group)
 
     # ------------------------------------------------------------------------------------------------
     def to(self, device=None, dtype=None):
@@ -167,7 +175,19 @@ class Pose2VideoPipeline:
         vid_bk = bk_lat.permute(1, 0, 2, 3).unsqueeze(0).to(dtype).contiguous()  # [1, 4, F, h, w]  :434-443
         mark("vae_encode")
 
-        pose_fea = self.pose_guider.forward_nhwc(inp["pose"]).reshape(F_, h * w, -1)  # channels-last, per frame
+        rank, world, group = self._shard
+        if world > 1:
+            import torch.distributed as dist
+            if F_ % world == 0:  # pose features: each rank computes its frames, then all-gather [F, hw, 320]
+                fl = F_ // world
+                loc = self.pose_guider.forward_nhwc(inp["pose"][:, :, rank * fl:(rank + 1) * fl].contiguous())
+                pose_all = torch.empty((world * loc.shape[0], loc.shape[1]), dtype=loc.dtype, device=device)
+                dist.all_gather_into_tensor(pose_all, loc.contiguous(), group=group)
+                pose_fea = pose_all.reshape(F_, h * w, -1)
+            else:
+                pose_fea = self.pose_guider.forward_nhwc(inp["pose"]).reshape(F_, h * w, -1)
+        else:
+            pose_fea = self.pose_guider.forward_nhwc(inp["pose"]).reshape(F_, h * w, -1)  # channels-last, per frame
         mark("pose_guider")
 
         # reference UNet once, banks -> denoising engine (pipeline :393-406, :480-490)
@@ -179,6 +199,7 @@ class Pose2VideoPipeline:
                             encoder_hidden_states=ehs, return_dict=False)
         reader.update(writer)
         den = self.denoising_unet.engine()
+        den.shard = (rank, world, group)
         mark("reference_unet")
 
         context_scheduler = get_context_scheduler(context_schedule)
@@ -187,15 +208,26 @@ class Pose2VideoPipeline:
         single = len(windows) == 1
         win_inputs = []
         for c in windows:  # the windows and their pose features are the same at every step (pipeline :493-500)
-            pose_in = pose_fea[c].reshape(1, len(c) * h * w, -1).repeat(rep, 1, 1).reshape(rep * len(c) * h * w, -1)
-            win_inputs.append((c, vid_bk[:, :, c], pose_in.contiguous()))
+            if world > 1:
+                if len(c) % world:
+                    raise NotImplementedError(f"a window of {len(c)} frames cannot be sharded over {world} GPUs")
+                fl = len(c) // world
+                cl = c[rank * fl:(rank + 1) * fl]  # this rank's frames of the window, in window order
+            else:
+                cl = c
+            pose_in = pose_fea[cl].reshape(1, len(cl) * h * w, -1).repeat(rep, 1, 1).reshape(rep * len(cl) * h * w, -1)
+            win_inputs.append((c, cl, vid_bk[:, :, cl], pose_in.contiguous()))
         for i, t in enumerate(timesteps):
             if not single:
                 noise_pred = torch.zeros((rep, 4, F_, h, w), device=device, dtype=dtype)
                 counter = torch.zeros((F_,), device=device, dtype=dtype)
-            for c, bk_c, pose_in in win_inputs:
-                lat_in = torch.cat([latents[:, :, c], bk_c], dim=1).repeat(rep, 1, 1, 1, 1)
+            for c, cl, bk_c, pose_in in win_inputs:
+                lat_in = torch.cat([latents[:, :, cl], bk_c], dim=1).repeat(rep, 1, 1, 1, 1)
                 pred = den.forward(lat_in, t, pose_in)
+                if world > 1:  # [rep, 4, f/world, h, w] per rank -> the window's full prediction on every rank
+                    parts = torch.empty((world,) + tuple(pred.shape), dtype=pred.dtype, device=device)
+                    dist.all_gather_into_tensor(parts, pred.contiguous(), group=group)
+                    pred = parts.permute(1, 2, 0, 3, 4, 5).reshape(rep, 4, len(c), h, w)
                 if single:
                     noise_pred, counter = pred, None
                 else:
@@ -214,7 +246,14 @@ class Pose2VideoPipeline:
         writer.clear()
         out = {"latents": latents}
         if decode:
-            out["videos"] = self.decode_latents_device(latents)
+            if world > 1 and F_ % world == 0:
+                fl = F_ // world
+                loc = self.decode_latents_device(latents[:, :, rank * fl:(rank + 1) * fl])  # [1, 3, fl, H, W]
+                parts = torch.empty((world,) + tuple(loc.shape), dtype=loc.dtype, device=device)
+                dist.all_gather_into_tensor(parts, loc.contiguous(), group=group)
+                out["videos"] = parts.permute(1, 2, 0, 3, 4, 5).reshape(1, 3, F_, loc.shape[-2], loc.shape[-1])
+            else:
+                out["videos"] = self.decode_latents_device(latents)
             mark("vae_decode")
         self._marks = marks
         self.last_latents = latents

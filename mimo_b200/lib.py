@@ -84,6 +84,19 @@ class AttnParams(C.Structure):
     ]
 
 
+class AttnTemporalParams(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ld_q", C.c_int64),
+        ("k", C.c_void_p), ("v", C.c_void_p), ("ld_kv", C.c_int64),
+        ("out", C.c_void_p), ("ld_out", C.c_int64),
+        ("chunk_stride_rows", C.c_int64),
+        ("batch", C.c_int32), ("q_frames", C.c_int32), ("kv_frames", C.c_int32), ("frames_per_chunk", C.c_int32),
+        ("hw", C.c_int32), ("heads", C.c_int32), ("d", C.c_int32),
+        ("scale", C.c_float),
+        ("dtype", C.c_int32),
+    ]
+
+
 # every symbol include/mimo_b200.h declares: name -> (restype, argtypes)
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SYMBOLS = {
@@ -96,9 +109,9 @@ SYMBOLS = {
     "mimo_conv3x3": (C.c_int, [C.POINTER(Conv3x3Params), _VP]),
     "mimo_im2col3x3": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I64, _I32, _VP]),
     "mimo_groupnorm": (C.c_int, [C.POINTER(GroupNormParams), _VP]),
-    "mimo_layernorm": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _F, _VP, _I64, _I32, _I32, _VP]),
+    "mimo_layernorm": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _F, _VP, _I64, _I32, _I32, _I32, _VP]),
     "mimo_attn_spatial": (C.c_int, [C.POINTER(AttnParams), _VP]),
-    "mimo_attn_temporal": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _F, _I32, _VP]),
+    "mimo_attn_temporal": (C.c_int, [C.POINTER(AttnTemporalParams), _VP]),
     "mimo_ncfhw_to_nhwc": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "mimo_nhwc_to_ncfhw": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "mimo_upsample2x": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
@@ -108,7 +121,7 @@ SYMBOLS = {
     "mimo_cfg_ddim_step": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _I64, _F, _F, _F, _F, _F, _I32, _VP]),
 }
 # test hook, not part of the public header
-_DEBUG_SYMBOLS = {"mimo_debug_force_bn": (C.c_int, [C.c_int])}
+_DEBUG_SYMBOLS = {"mimo_debug_force_bn": (C.c_int, [C.c_int]), "mimo_debug_attn_variant": (C.c_int, [C.c_int])}
 
 _lib = None
 
@@ -128,7 +141,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
         fn.restype = res
         fn.argtypes = args
-    for which, st in enumerate((Epilogue, GemmParams, Conv3x3Params, GroupNormParams, AttnParams)):
+    for which, st in enumerate((Epilogue, GemmParams, Conv3x3Params, GroupNormParams, AttnParams, AttnTemporalParams)):
         if lib.mimo_abi_sizeof(which) != C.sizeof(st):
             raise MimoError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes in lib.py but "
                             f"{lib.mimo_abi_sizeof(which)} in {LIB_PATH.name}; rebuild the library")

@@ -172,13 +172,14 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int,
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps=1e-5, pe: Optional[torch.Tensor] = None,
-              rows_per_frame=1, frames=1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              rows_per_frame=1, frames=1, pe_frame_offset=0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     assert x.is_contiguous() and x.dim() == 2
     if out is None:
         out = torch.empty_like(x)
     with _Call("layernorm", 1, 0.0, 2.0 * 2 * x.numel()):
         L.check(L.load().mimo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), x.shape[0], x.shape[1], float(eps),
-                                        _ptr(pe), int(rows_per_frame), int(frames), _dt(x), _stream()), "mimo_layernorm")
+                                        _ptr(pe), int(rows_per_frame), int(frames), int(pe_frame_offset), _dt(x),
+                                        _stream()), "mimo_layernorm")
     return out
 
 
@@ -219,16 +220,29 @@ def attn_spatial(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n: int, lq: 
 
 
 def attn_temporal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, frames: int, hw: int, heads: int, *,
-                  scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  scale: Optional[float] = None, out: Optional[torch.Tensor] = None, q_frames: Optional[int] = None,
+                  frames_per_chunk: Optional[int] = None, chunk_stride_rows: int = 0) -> torch.Tensor:
+    """q: [batch*q_frames*hw, C]; k/v: column slices of one buffer holding all `frames` frames, possibly as
+    frames/frames_per_chunk chunks chunk_stride_rows apart (frame-sharded clip, see the header)."""
     Cdim = q.shape[1]
     d = Cdim // heads
+    fq = frames if q_frames is None else q_frames
     if out is None:
-        out = torch.empty((batch * frames * hw, Cdim), dtype=q.dtype, device=q.device)
-    rows = batch * frames * hw
-    with _Call("attn_temporal", 1, 4.0 * rows * frames * Cdim, 2.0 * 4 * rows * Cdim):
-        L.check(L.load().mimo_attn_temporal(_ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0), batch,
-                                            frames, hw, heads, d, float(scale if scale is not None else d ** -0.5),
-                                            _dt(q), _stream()), "mimo_attn_temporal")
+        out = torch.empty((batch * fq * hw, Cdim), dtype=q.dtype, device=q.device)
+    p = L.AttnTemporalParams()
+    p.q, p.ld_q = _ptr(q), q.stride(0)
+    p.k, p.v, p.ld_kv = _ptr(k), _ptr(v), k.stride(0)
+    assert k.stride(0) == v.stride(0)
+    p.out, p.ld_out = _ptr(out), out.stride(0)
+    p.chunk_stride_rows = int(chunk_stride_rows)
+    p.batch, p.q_frames, p.kv_frames = batch, fq, frames
+    p.frames_per_chunk = frames if frames_per_chunk is None else frames_per_chunk
+    p.hw, p.heads, p.d = hw, heads, d
+    p.scale = float(scale if scale is not None else d ** -0.5)
+    p.dtype = _dt(q)
+    rows = batch * fq * hw
+    with _Call("attn_temporal", 1, 4.0 * rows * frames * Cdim, 2.0 * (2 * rows + 2 * batch * frames * hw) * Cdim):
+        L.check(L.load().mimo_attn_temporal(C.byref(p), _stream()), "mimo_attn_temporal")
     return out
 
 
