@@ -1,5 +1,5 @@
 // Shared declarations of the spatial-attention kernels (attn_spatial.cu: one Q tile per CTA, any head dim up to 192;
-// attn_spatial_pp.cu: two Q tiles per CTA in ping-pong, head dim <= 64).
+// attn_spatial_pp.cu: two Q tiles per CTA in ping-pong, head dim <= 128).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -19,7 +19,7 @@ struct AttnArgs {
   long long ld_out;
 };
 
-// two Q tiles per CTA (grid.x = ceil(lq / 256)); dp <= 64
+// two Q tiles per CTA (grid.x = ceil(lq / 256)); dp <= 128
 int launch_attn_pp(bool bf16, const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& bk,
                    const CUtensorMap& bv, const AttnArgs& a, int n, cudaStream_t st);
 

@@ -21,11 +21,19 @@
 namespace mimo {
 
 constexpr int kPPThreads = 384;
-constexpr int kPPQBytes = 2 * kChunkBytes;        // Q_A, Q_B
-constexpr int kPPKVStage = 2 * kChunkBytes;       // K then V
-constexpr int kPPPBytes = 2 * 2 * kChunkBytes;    // P_A, P_B (two 64-key chunks each)
-constexpr int kPPSmem = kPPQBytes + 2 * kPPKVStage + kPPPBytes + 256;
-constexpr float kRescaleThreshold = 8.0f;         // log2 units
+constexpr int kPPPBytes = 2 * 2 * kChunkBytes;  // P_A, P_B (two 64-key chunks each)
+constexpr float kRescaleThreshold = 8.0f;       // log2 units
+
+// NCH = 64-element chunks of the head dim (1: d <= 64, 2: d <= 128). K and V tiles live in separate rings with their
+// own barriers: a K stage is released as soon as both query tiles have issued Q.K^T on it, a V stage after both P.V,
+// so even single-stage rings (NCH = 2, where shared memory is tight) keep TMA one tile ahead of the tensor pipe.
+template <int NCH>
+struct PPCfg {
+  static constexpr int kStages = NCH == 1 ? 2 : 1;
+  static constexpr int kTile = NCH * kChunkBytes;  // one 128-row K or V (or Q) tile
+  static constexpr int kQBytes = 2 * kTile;
+  static constexpr int kSmem = kQBytes + 2 * kStages * kTile + kPPPBytes + 256;
+};
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -33,24 +41,29 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-template <bool kBf16>
+template <int NCH, bool kBf16>
 __global__ void __launch_bounds__(kPPThreads, 1)
 attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
                        const __grid_constant__ CUtensorMap tmBV, AttnArgs a) {
   using C = Cvt<kBf16>;
+  using Cfg = PPCfg<NCH>;
+  constexpr int ST = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + kPPQBytes;
-  uint8_t* sP = sKV + 2 * kPPKVStage;
+  uint8_t* sK = sQ + Cfg::kQBytes;
+  uint8_t* sV = sK + ST * Cfg::kTile;
+  uint8_t* sP = sV + ST * Cfg::kTile;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPPPBytes);
-  uint64_t* q_full = bars;           // 1
-  uint64_t* kv_full = bars + 1;      // 2
-  uint64_t* kv_empty = bars + 3;     // 2
-  uint64_t* s_full = bars + 5;       // 2 (per query tile)
-  uint64_t* p_full = bars + 7;       // 2
-  uint64_t* o_done = bars + 9;       // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* k_full = bars + 1;      // ST (<= 2)
+  uint64_t* k_empty = bars + 3;     // ST
+  uint64_t* v_full = bars + 5;      // ST
+  uint64_t* v_empty = bars + 7;     // ST
+  uint64_t* s_full = bars + 9;      // 2 (per query tile)
+  uint64_t* p_full = bars + 11;     // 2
+  uint64_t* o_done = bars + 13;     // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,9 +84,13 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 128);
       mbar_init(&o_done[s], 1);
@@ -85,23 +102,32 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)
+  // columns: S_A [0,128)  S_B [128,256)  O_A [256,384)  O_B [384,512)
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    mbar_expect_tx(q_full, kPPQBytes);
-    tma_load_4d(sQ, &tmQ, q_full, 0, h, q_pair * 2 * BQ, n);
-    tma_load_4d(sQ + kChunkBytes, &tmQ, q_full, 0, h, q_pair * 2 * BQ + BQ, n);
+    mbar_expect_tx(q_full, Cfg::kQBytes);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      tma_load_4d(sQ + ch * kChunkBytes, &tmQ, q_full, ch * 64, h, q_pair * 2 * BQ, n);
+      tma_load_4d(sQ + Cfg::kTile + ch * kChunkBytes, &tmQ, q_full, ch * 64, h, q_pair * 2 * BQ + BQ, n);
+    }
     for (int j = 0; j < T; ++j) {
-      const int stage = j & 1;
-      mbar_wait(&kv_empty[stage], ((j >> 1) & 1u) ^ 1u);
-      uint8_t* sk = sKV + stage * kPPKVStage;
-      mbar_expect_tx(&kv_full[stage], kPPKVStage);
+      const int stage = j % ST;
+      const uint32_t ph = ((j / ST) & 1u) ^ 1u;
       const bool bank = j >= a.n_self_tiles;
       const int row0 = (bank ? j - a.n_self_tiles : j) * BKV;
       const int img = bank ? bidx : n;
-      tma_load_4d(sk, bank ? &tmBK : &tmK, &kv_full[stage], 0, h, row0, img);
-      tma_load_4d(sk + kChunkBytes, bank ? &tmBV : &tmV, &kv_full[stage], 0, h, row0, img);
+      mbar_wait(&k_empty[stage], ph);
+      mbar_expect_tx(&k_full[stage], Cfg::kTile);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+        tma_load_4d(sK + stage * Cfg::kTile + ch * kChunkBytes, bank ? &tmBK : &tmK, &k_full[stage], ch * 64, h, row0, img);
+      mbar_wait(&v_empty[stage], ph);
+      mbar_expect_tx(&v_full[stage], Cfg::kTile);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+        tma_load_4d(sV + stage * Cfg::kTile + ch * kChunkBytes, bank ? &tmBV : &tmV, &v_full[stage], ch * 64, h, row0, img);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
@@ -111,36 +137,40 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t q_addr = smem_u32(sQ);
     const uint32_t p_addr = smem_u32(sP);
     auto issue_qk = [&](int x, int j) {
-      const uint32_t k_addr = smem_u32(sKV + (j & 1) * kPPKVStage);
-      const uint32_t qa = q_addr + x * kChunkBytes;
-      for (int ks = 0; ks < ksteps_qk; ++ks)
-        umma_ss(tmem_base + x * 128, make_smem_desc_sw128(qa + ks * 32, 16, 1024),
-                make_smem_desc_sw128(k_addr + ks * 32, 16, 1024), idesc_qk, ks != 0 ? 1u : 0u);
+      const uint32_t k_addr = smem_u32(sK + (j % ST) * Cfg::kTile);
+      const uint32_t qa = q_addr + x * Cfg::kTile;
+      for (int ks = 0; ks < ksteps_qk; ++ks) {
+        const uint32_t off = (ks >> 2) * kChunkBytes + (ks & 3) * 32;
+        umma_ss(tmem_base + x * 128, make_smem_desc_sw128(qa + off, 16, 1024),
+                make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0 ? 1u : 0u);
+      }
       tc_commit(&s_full[x]);
+      if (x == 1) tc_commit(&k_empty[j % ST]);  // both query tiles have consumed K[j]
     };
     mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
+    mbar_wait(&k_full[0], 0);
     tc_fence_after();
     issue_qk(0, 0);
     issue_qk(1, 0);
     for (int j = 0; j < T; ++j) {
-      const int stage = j & 1;
-      const uint32_t v_addr = smem_u32(sKV + stage * kPPKVStage + kChunkBytes);
+      const int stage = j % ST;
+      const uint32_t v_addr = smem_u32(sV + stage * Cfg::kTile);
       for (int x = 0; x < 2; ++x) {
         mbar_wait(&p_full[x], j & 1);
+        if (x == 0) mbar_wait(&v_full[stage], (j / ST) & 1u);
         tc_fence_after();
         const uint32_t pa0 = p_addr + x * 2 * kChunkBytes;
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
           const uint32_t pa = pa0 + (ks >> 2) * kChunkBytes + (ks & 3) * 32;
-          umma_ss(tmem_base + 256 + x * 64, make_smem_desc_sw128(pa, 16, 1024),
+          umma_ss(tmem_base + 256 + x * 128, make_smem_desc_sw128(pa, 16, 1024),
                   make_smem_desc_sw128(v_addr + ks * 2048, kChunkBytes, 1024), idesc_pv, (j | ks) != 0 ? 1u : 0u);
         }
-        if (x == 1) tc_commit(&kv_empty[stage]);  // both query tiles are done with K[j] and V[j]
+        if (x == 1) tc_commit(&v_empty[stage]);  // both query tiles are done with V[j]
         tc_commit(&o_done[x]);
         if (j + 1 < T) {
           if (x == 0) {
-            mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1u);
+            mbar_wait(&k_full[(j + 1) % ST], ((j + 1) / ST) & 1u);
             tc_fence_after();
           }
           issue_qk(x, j + 1);
@@ -154,7 +184,7 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int r = ew * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
     const uint32_t tS = tmem_base + x * 128 + lane_off;
-    const uint32_t tO = tmem_base + 256 + x * 64 + lane_off;
+    const uint32_t tO = tmem_base + 256 + x * 128 + lane_off;
     uint8_t* prow = sP + x * 2 * kChunkBytes + r * 128;
     const int sw = r & 7;
     const float sc = a.scale_log2;
@@ -306,23 +336,28 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
-int launch_attn_pp(bool bf16, const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& bk,
-                   const CUtensorMap& bv, const AttnArgs& a, int n, cudaStream_t st) {
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[bf16 ? 1 : 0]) {
-    cudaError_t e = bf16 ? cudaFuncSetAttribute(attn_spatial_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPPSmem)
-                         : cudaFuncSetAttribute(attn_spatial_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPPSmem);
+template <int NCH, bool kBf16>
+static int launch_pp(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& bk,
+                     const CUtensorMap& bv, const AttnArgs& a, int n, cudaStream_t st) {
+  using Cfg = PPCfg<NCH>;
+  auto kern = attn_spatial_pp_kernel<NCH, kBf16>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_pp)", e);
-    attr_done[bf16 ? 1 : 0] = true;
+    attr_done = true;
   }
   dim3 grid((a.lq + 2 * BQ - 1) / (2 * BQ), a.heads, n);
-  if (bf16)
-    attn_spatial_pp_kernel<true><<<grid, kPPThreads, kPPSmem, st>>>(q, k, v, bk, bv, a);
-  else
-    attn_spatial_pp_kernel<false><<<grid, kPPThreads, kPPSmem, st>>>(q, k, v, bk, bv, a);
+  kern<<<grid, kPPThreads, Cfg::kSmem, st>>>(q, k, v, bk, bv, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("attn_pp launch", e);
   return MIMO_OK;
+}
+
+int launch_attn_pp(bool bf16, const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& bk,
+                   const CUtensorMap& bv, const AttnArgs& a, int n, cudaStream_t st) {
+  if (a.dp <= 64) return bf16 ? launch_pp<1, true>(q, k, v, bk, bv, a, n, st) : launch_pp<1, false>(q, k, v, bk, bv, a, n, st);
+  return bf16 ? launch_pp<2, true>(q, k, v, bk, bv, a, n, st) : launch_pp<2, false>(q, k, v, bk, bv, a, n, st);
 }
 
 }  // namespace mimo

@@ -225,9 +225,9 @@ class Pose2VideoPipeline:
                 lat_in = torch.cat([latents[:, :, cl], bk_c], dim=1).repeat(rep, 1, 1, 1, 1)
                 pred = den.forward(lat_in, t, pose_in)
                 if world > 1:  # [rep, 4, f/world, h, w] per rank -> the window's full prediction on every rank
-                    parts = torch.empty((world,) + tuple(pred.shape), dtype=pred.dtype, device=device)
-                    dist.all_gather_into_tensor(parts, pred.contiguous(), group=group)
-                    pred = parts.permute(1, 2, 0, 3, 4, 5).reshape(rep, 4, len(c), h, w)
+                    parts = torch.empty((world * pred.shape[0],) + tuple(pred.shape[1:]), dtype=pred.dtype, device=device)
+                    dist.all_gather_into_tensor(parts, pred.contiguous(), group=group)  # concatenated along dim 0
+                    pred = parts.view((world,) + tuple(pred.shape)).permute(1, 2, 0, 3, 4, 5).reshape(rep, 4, len(c), h, w)
                 if single:
                     noise_pred, counter = pred, None
                 else:
@@ -249,9 +249,10 @@ class Pose2VideoPipeline:
             if world > 1 and F_ % world == 0:
                 fl = F_ // world
                 loc = self.decode_latents_device(latents[:, :, rank * fl:(rank + 1) * fl])  # [1, 3, fl, H, W]
-                parts = torch.empty((world,) + tuple(loc.shape), dtype=loc.dtype, device=device)
+                parts = torch.empty((world * loc.shape[0],) + tuple(loc.shape[1:]), dtype=loc.dtype, device=device)
                 dist.all_gather_into_tensor(parts, loc.contiguous(), group=group)
-                out["videos"] = parts.permute(1, 2, 0, 3, 4, 5).reshape(1, 3, F_, loc.shape[-2], loc.shape[-1])
+                out["videos"] = parts.view((world,) + tuple(loc.shape)).permute(1, 2, 0, 3, 4, 5).reshape(
+                    1, 3, F_, loc.shape[-2], loc.shape[-1])
             else:
                 out["videos"] = self.decode_latents_device(latents)
             mark("vae_decode")

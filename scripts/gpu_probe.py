@@ -271,6 +271,10 @@ def spatial_shapes():
     ok &= spatial_case(4, 64, 8, 160, lb=64, bank_idx=[-1, -1, 1, 1])
     ok &= spatial_case(2, 576, 8, 40, lb=576, bank_idx=[-1, 1])   # 24x24: ragged tiles
     ok &= spatial_case(1, 4096, 8, 40, lb=4096, bank_idx=[1])
+    ok &= spatial_case(2, 320, 8, 80, lb=320, bank_idx=[1, -1])   # d=80 ping-pong kernel, ragged tiles
+    ok &= spatial_case(1, 200, 4, 128)                             # dp = 128, second query tile partly out of range
+    ok &= spatial_case(3, 130, 8, 16, lb=70, bank_idx=[0, -1, 1])  # tiny head dim, ragged bank
+    ok &= spatial_case(2, 64, 8, 32, lb=64, bank_idx=[-1, 1])      # whole second query tile out of range
     return ok
 
 
