@@ -1,11 +1,13 @@
 // Motion-module temporal self-attention: for every (batch b, pixel p, head h) an Fq x F attention over the
 // frame axis (F <= 32, head dim d a multiple of 8).
 //
-// One CTA per (b, p): its 8 (= heads) warps stage the K and V rows of all F frames of that pixel in shared
-// memory with 128-bit loads (each row is C contiguous elements), then warp h / lane j computes query row j of
-// head h: scores against the F keys (K rows are smem broadcasts), fp32 softmax, and the PV product 8 output
-// channels at a time. The "(b f) d c <-> (b d) f c" transposes of the reference never materialise: frames are
-// addressed by stride. The op is ~0.2 % of the UNet's FLOPs and HBM/latency bound, hence CUDA cores.
+// The problems are tiny (24 x 24 x 40) but there are 65 536 of them per call at the 64x64 level, so the kernel is
+// organised around memory: one CTA stages the Q, K and V rows of all frames of one pixel (for a group of heads) in
+// shared memory with 128-bit loads — every row is a contiguous C-element segment, so the reference's
+// "(b f) d c <-> (b d) f c" transposes never materialise — and one warp per head then runs the attention on tensor
+// cores with warp-level mma.sync.m16n8k16 (a 24-row problem cannot fill a 128-row tcgen05 tile): S = Q K^T from
+// ldmatrix fragments, fp32 softmax in the accumulator registers, P re-used in registers as the A operand of P V,
+// V read with ldmatrix.trans. Outputs are staged through shared memory for 128-bit stores.
 //
 // Frame sharding: with the clip's frames split over G GPUs the queries are the Fq local frames while K/V cover all
 // F frames, stored as G chunks of frames_per_chunk frames each (the all-gathered per-rank buffers):
@@ -25,102 +27,192 @@ struct TemporalArgs {
   void* out;
   long long ld_q, ld_kv, ld_out, chunk_stride_rows;
   int Fq, F, fpc, hw, heads, d;
-  float scale;
+  int dpad;    // d rounded up to 16 (K dimension of Q K^T)
+  int hg;      // heads per CTA
+  int pitch;   // smem row pitch in elements: hg * dpad + 8 (the +8 keeps ldmatrix rows on distinct banks)
+  float scale_log2;
 };
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+template <bool kBf16>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (kBf16) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                 "{%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                 "{%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
 
 template <bool kBf16>
 __global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a) {
   using C = Cvt<kBf16>;
   using T = typename C::T;
-  extern __shared__ uint4 smem_kv[];  // K[F][Cdim] then V[F][Cdim], 16-bit
-  const int Cdim = a.heads * a.d;
-  const int vecs = Cdim / 8;
-  T* sk = reinterpret_cast<T*>(smem_kv);
-  T* sv = sk + static_cast<size_t>(a.F) * Cdim;
-  const int b = blockIdx.x / a.hw;
-  const int p = blockIdx.x % a.hw;
+  extern __shared__ uint4 smem_qkv[];
+  T* sq = reinterpret_cast<T*>(smem_qkv);           // [32][pitch]
+  T* sk = sq + 32 * a.pitch;                         // [32][pitch]
+  T* sv = sk + 32 * a.pitch;                         // [32][pitch]
+  const int groups = a.heads / a.hg;
+  const int hg0 = (blockIdx.x % groups) * a.hg;      // first head of this CTA
+  const int bp = blockIdx.x / groups;
+  const int b = bp / a.hw;
+  const int p = bp % a.hw;
+  const int d = a.d, dpad = a.dpad, pitch = a.pitch;
+  const int dv = d / 8;                              // 16-byte vectors per head row
+  const int vec_row = a.hg * dv;
 
-  for (int i = threadIdx.x; i < a.F * vecs; i += blockDim.x) {
-    const int f = i / vecs, cv = i % vecs;
+  // ---- stage Q (Fq rows), K, V (F rows) of this pixel; zero what the MMAs read beyond the data ----
+  for (int i = threadIdx.x; i < a.Fq * vec_row; i += blockDim.x) {
+    const int f = i / vec_row, rem = i % vec_row, hh = rem / dv, pc = rem % dv;
+    const long long row = (static_cast<long long>(b) * a.Fq + f) * a.hw + p;
+    *reinterpret_cast<uint4*>(sq + f * pitch + hh * dpad + pc * 8) =
+        *reinterpret_cast<const uint4*>(static_cast<const T*>(a.q) + row * a.ld_q + (hg0 + hh) * d + pc * 8);
+  }
+  for (int i = threadIdx.x; i < a.F * vec_row; i += blockDim.x) {
+    const int f = i / vec_row, rem = i % vec_row, hh = rem / dv, pc = rem % dv;
     const long long row = static_cast<long long>(f / a.fpc) * a.chunk_stride_rows +
                           (static_cast<long long>(b) * a.fpc + f % a.fpc) * a.hw + p;
-    const long long off = row * a.ld_kv + cv * 8;
-    reinterpret_cast<uint4*>(sk)[i] = *reinterpret_cast<const uint4*>(static_cast<const T*>(a.k) + off);
-    reinterpret_cast<uint4*>(sv)[i] = *reinterpret_cast<const uint4*>(static_cast<const T*>(a.v) + off);
+    const long long off = row * a.ld_kv + (hg0 + hh) * d + pc * 8;
+    *reinterpret_cast<uint4*>(sk + f * pitch + hh * dpad + pc * 8) =
+        *reinterpret_cast<const uint4*>(static_cast<const T*>(a.k) + off);
+    *reinterpret_cast<uint4*>(sv + f * pitch + hh * dpad + pc * 8) =
+        *reinterpret_cast<const uint4*>(static_cast<const T*>(a.v) + off);
+  }
+  if (dpad > d) {  // zero the K-dimension padding of Q and K (d = 40 -> 48)
+    const int padv = (dpad - d) / 8;
+    for (int i = threadIdx.x; i < 32 * a.hg * padv; i += blockDim.x) {
+      const int f = i / (a.hg * padv), rem = i % (a.hg * padv), hh = rem / padv, pc = rem % padv;
+      *reinterpret_cast<uint4*>(sq + f * pitch + hh * dpad + d + pc * 8) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sk + f * pitch + hh * dpad + d + pc * 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  // V rows beyond F multiply probabilities that are exactly 0: they must be finite -> zero them
+  for (int i = threadIdx.x; i < (32 - a.F) * (pitch / 8); i += blockDim.x) {
+    const int f = a.F + i / (pitch / 8), pc = i % (pitch / 8);
+    *reinterpret_cast<uint4*>(sv + f * pitch + pc * 8) = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
 
-  const int h = threadIdx.x >> 5;
-  const int j = threadIdx.x & 31;
-  if (h >= a.heads || j >= a.Fq) return;
-  const int F = a.F, d = a.d;
-  const long long qtok = (static_cast<long long>(b) * a.Fq + j) * a.hw + p;
+  const int hh = threadIdx.x >> 5;  // head within the group
+  const int lane = threadIdx.x & 31;
+  if (hh >= a.hg) return;
+  const int g = lane >> 2, t = lane & 3;
+  const int MT = (a.Fq + 15) >> 4;  // 16-row query tiles
+  const int NT = (a.F + 7) >> 3;    // 8-key tiles
+  const T* qh = sq + hh * dpad;
+  const T* kh = sk + hh * dpad;
+  const T* vh = sv + hh * dpad;
 
-  const T* qrow = static_cast<const T*>(a.q) + qtok * a.ld_q + h * d;
-  float s[32];
+  // ---- S = Q K^T ----
+  float s[2][4][4];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) s[i] = 0.f;
-  for (int c8 = 0; c8 < d / 8; ++c8) {
-    const uint4 uq = *reinterpret_cast<const uint4*>(qrow + c8 * 8);
-    const uint32_t wq[4] = {uq.x, uq.y, uq.z, uq.w};
-    float q[8];
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 v2 = C::unpack(wq[t]);
-      q[2 * t] = v2.x;
-      q[2 * t + 1] = v2.y;
-    }
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < F) {
-        const uint4 uk = *reinterpret_cast<const uint4*>(sk + static_cast<size_t>(i) * Cdim + h * d + c8 * 8);
-        const uint32_t wk[4] = {uk.x, uk.y, uk.z, uk.w};
+      for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+  for (int ks = 0; ks < dpad / 16; ++ks) {
+    uint32_t af[2][4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 v2 = C::unpack(wk[t]);
-          s[i] = fmaf(q[2 * t], v2.x, s[i]);
-          s[i] = fmaf(q[2 * t + 1], v2.y, s[i]);
+    for (int mt = 0; mt < 2; ++mt)
+      if (mt < MT) ldsm_x4(af[mt], qh + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * pitch + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {  // pairs of key tiles
+      if (np * 2 < NT) {
+        uint32_t bf[4];
+        ldsm_x4(bf, kh + (np * 16 + (lane & 7) + (lane >> 4) * 8) * pitch + ks * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt < MT) {
+            mma16816<kBf16>(s[mt][np * 2], af[mt], bf[0], bf[1]);
+            if (np * 2 + 1 < NT) mma16816<kBf16>(s[mt][np * 2 + 1], af[mt], bf[2], bf[3]);
+          }
         }
       }
     }
   }
-  float m = -INFINITY;
+
+  // ---- softmax over the F keys (rows g and g + 8 of each query tile live in this thread's quad) ----
+  float inv_sum[2][2];
+  uint32_t pf[2][2][4];  // P as A fragments: [query tile][16-key step]
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (i < F) {
-      s[i] *= a.scale;
-      m = fmaxf(m, s[i]);
-    }
-  float sum = 0.f;
+  for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (i < F) {
-      s[i] = __expf(s[i] - m);
-      sum += s[i];
-    }
-  const float inv = 1.0f / sum;
-  T* orow = static_cast<T*>(a.out) + qtok * a.ld_out + h * d;
-  for (int c8 = 0; c8 < d / 8; ++c8) {
-    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int half = 0; half < 2; ++half) {  // half 0: row g, half 1: row g + 8
+      float m = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < F) {
-        const uint4 uv = *reinterpret_cast<const uint4*>(sv + static_cast<size_t>(i) * Cdim + h * d + c8 * 8);
-        const uint32_t wv[4] = {uv.x, uv.y, uv.z, uv.w};
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 v2 = C::unpack(wv[t]);
-          o[2 * t] = fmaf(s[i], v2.x, o[2 * t]);
-          o[2 * t + 1] = fmaf(s[i], v2.y, o[2 * t + 1]);
+        for (int e = 0; e < 2; ++e) {
+          const int col = nt * 8 + 2 * t + e;
+          float& v = s[mt][nt][half * 2 + e];
+          v = (col < a.F) ? v * a.scale_log2 : -INFINITY;
+          m = fmaxf(m, v);
         }
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float& v = s[mt][nt][half * 2 + e];
+          v = exp2f(v - m);  // exp2f(-inf) = 0 for the masked keys
+          sum += v;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      inv_sum[mt][half] = 1.0f / sum;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      pf[mt][kk][0] = C::pack(s[mt][2 * kk][0], s[mt][2 * kk][1]);
+      pf[mt][kk][1] = C::pack(s[mt][2 * kk][2], s[mt][2 * kk][3]);
+      pf[mt][kk][2] = C::pack(s[mt][2 * kk + 1][0], s[mt][2 * kk + 1][1]);
+      pf[mt][kk][3] = C::pack(s[mt][2 * kk + 1][2], s[mt][2 * kk + 1][3]);
+    }
+  }
+
+  // ---- O = P V, eight output channels at a time; results overwrite this head's (already consumed) Q columns ----
+  __syncwarp();
+  T* oh = sq + hh * dpad;
+  const int KK = (a.F + 15) >> 4;
+  for (int nd = 0; nd < dv; ++nd) {
+    uint32_t bv[4];
+    ldsm_x4_trans(bv, vh + lane * pitch + nd * 8);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      if (mt < MT) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816<kBf16>(o, pf[mt][0], bv[0], bv[1]);
+        if (KK > 1) mma16816<kBf16>(o, pf[mt][1], bv[2], bv[3]);
+        *reinterpret_cast<uint32_t*>(oh + (mt * 16 + g) * pitch + nd * 8 + 2 * t) =
+            C::pack(o[0] * inv_sum[mt][0], o[1] * inv_sum[mt][0]);
+        *reinterpret_cast<uint32_t*>(oh + (mt * 16 + g + 8) * pitch + nd * 8 + 2 * t) =
+            C::pack(o[2] * inv_sum[mt][1], o[3] * inv_sum[mt][1]);
       }
     }
-    uint4 w;
-    w.x = C::pack(o[0] * inv, o[1] * inv);
-    w.y = C::pack(o[2] * inv, o[3] * inv);
-    w.z = C::pack(o[4] * inv, o[5] * inv);
-    w.w = C::pack(o[6] * inv, o[7] * inv);
-    *reinterpret_cast<uint4*>(orow + c8 * 8) = w;
+  }
+  __syncwarp();
+  for (int i = lane; i < a.Fq * dv; i += 32) {
+    const int f = i / dv, pc = i % dv;
+    const long long row = (static_cast<long long>(b) * a.Fq + f) * a.hw + p;
+    *reinterpret_cast<uint4*>(static_cast<T*>(a.out) + row * a.ld_out + (hg0 + hh) * d + pc * 8) =
+        *reinterpret_cast<const uint4*>(oh + f * pitch + pc * 8);
   }
 }
 
@@ -136,8 +228,6 @@ extern "C" int mimo_attn_temporal(const mimo_attn_temporal_params* p, void* stre
       (p->kv_frames % fpc))
     return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: need frames <= 32, heads <= 32, d % 8 == 0, kv_frames % chunk == 0");
   if (int rc = ensure_device()) return rc;
-  const size_t smem = static_cast<size_t>(2) * p->kv_frames * p->heads * p->d * 2;
-  if (smem > 227 * 1024) return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: K/V tile exceeds shared memory");
   TemporalArgs a;
   a.q = p->q;
   a.k = p->k;
@@ -153,10 +243,21 @@ extern "C" int mimo_attn_temporal(const mimo_attn_temporal_params* p, void* stre
   a.hw = p->hw;
   a.heads = p->heads;
   a.d = p->d;
-  a.scale = p->scale;
+  a.dpad = (p->d + 15) / 16 * 16;
+  a.scale_log2 = p->scale * 1.4426950408889634f;
+  // heads per CTA: as many as keep the Q/K/V staging under ~100 KB (several CTAs per SM)
+  int hg = p->heads;
+  auto smem_for = [&](int h) { return static_cast<size_t>(3) * 32 * (h * a.dpad + 8) * 2; };
+  while (hg > 1 && (hg % 2 == 0) && smem_for(hg) > 100 * 1024) hg /= 2;
+  if (smem_for(hg) > 227 * 1024) return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: head dim too large");
+  a.hg = hg;
+  a.pitch = hg * a.dpad + 8;
+  const size_t smem = smem_for(hg);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int threads = p->heads * 32;
-  const unsigned grid = static_cast<unsigned>(p->batch) * p->hw;
+  const int threads = hg * 32;
+  const long long nblk = static_cast<long long>(p->batch) * p->hw * (p->heads / hg);
+  if (nblk > 0x7fffffffLL) return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: grid too large");
+  const unsigned grid = static_cast<unsigned>(nblk);
   static bool attr_done[2] = {false, false};
   cudaError_t e;
   if (p->dtype == MIMO_BF16) {

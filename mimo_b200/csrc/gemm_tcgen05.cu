@@ -8,7 +8,8 @@
 //   warp 1 lane 0 : MMA issuer    - tcgen05.mma.cta_group::1.kind::f16 128xBNx16, accumulators double-buffered
 //                                   in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
 //   warp 2        : TMEM allocator
-//   warps 4..7    : epilogue      - tcgen05.ld 32 lanes x 32 columns, fused bias / per-frame vector / residual /
+//   warps 4..11   : epilogue      - tcgen05.ld 32 lanes x 32 columns (two warp groups split the columns), software
+//                                   pipelined with the residual loads; fused bias / per-frame vector / residual /
 //                                   scale / SiLU / GEGLU, 16-byte vector stores
 // Convolution mode replaces the A loads by 4-D TMA boxes {64 ch, TW, TH, TN} over the NHWC input, one box per
 // (tap, 64-channel block, source tensor); TMA's out-of-bounds zero fill is the conv's zero padding and also
@@ -24,7 +25,7 @@ namespace mimo {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = one 128-byte swizzle row
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;
 
 struct EpiArgs {
   const void* bias;
@@ -90,7 +91,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);
+      mbar_init(&tmem_empty[b], 8);
     }
     fence_mbar_init();
   }
@@ -174,9 +175,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (8 warps) =====================
+    // warp w may only touch TMEM lanes [32*(w%4), +32): warps 4-7 and 8-11 each cover all 128 rows; the two groups
+    // split the tile's 32-column chunks between them. Per warp the chunk loop is software pipelined: the TMEM load
+    // and the residual loads of chunk i+1 are in flight while chunk i is converted and stored, and the first
+    // residual chunk is requested before the accumulator is even complete.
+    const int ew = warp & 3;
+    const int hsel = (warp - 4) >> 2;
     const int r = ew * 32 + lane;
+    constexpr int NCHUNK = BN / 32;
+    constexpr int H0 = (NCHUNK + 1) / 2;
+    using T = typename C::T;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int m_tile = tile / num_n_tiles;
@@ -197,118 +206,156 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         row_ok = (n < g.TN) && (x0 + x < g.W) && (y0 + y < g.H) && (n0 + n < g.NI);
         row = (static_cast<long long>(n0 + n) * g.H + (y0 + y)) * g.W + (x0 + x);
       }
-      const long long grp = ep.rowvec ? row / ep.rows_per_group : 0;
-
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 
       if (ep.act != MIMO_ACT_GEGLU) {
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_x32(taddr + c * 32, v);
-          tmem_ld_wait();
+        const int cbase = hsel ? H0 : 0;
+        const int ccount = hsel ? NCHUNK - H0 : H0;
+        const long long grp = ep.rowvec ? row / ep.rows_per_group : 0;
+        const T* rv = ep.rowvec ? static_cast<const T*>(ep.rowvec) + grp * ep.ld_rowvec : nullptr;
+        const T* res = (ep.residual && row_ok) ? static_cast<const T*>(ep.residual) + row * ep.ld_res : nullptr;
+        T* outp = static_cast<T*>(ep.out) + row * ep.ldo;
+        uint4 rbuf[2][4];
+        uint32_t vbuf[2][32];
+        auto load_res = [&](int c, uint4 (&dst)[4]) {
           const int col0 = n_tile * BN + c * 32;
-          if (row_ok) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int col = col0 + q * 8;
-              if (col < N) {  // N % 8 == 0
-                float f[8];
+          for (int q = 0; q < 4; ++q) {
+            dst[q] = make_uint4(0, 0, 0, 0);
+            if (res && col0 + q * 8 < N) dst[q] = *reinterpret_cast<const uint4*>(res + col0 + q * 8);
+          }
+        };
+        if (res) {  // pull the rest of this thread's residual row segment towards L2 while the main loop still runs
+          const int c_lo = n_tile * BN + cbase * 32;
+          int c_hi = c_lo + ccount * 32;
+          if (c_hi > N) c_hi = N;
+          for (int cc = c_lo + 64; cc < c_hi; cc += 64)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(res + cc));
+        }
+        if (ccount > 0) load_res(cbase, rbuf[0]);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if (ccount > 0) tmem_ld_x32(taddr + cbase * 32, vbuf[0]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
-                if (ep.bias) {
-                  const uint4 b = __ldg(reinterpret_cast<const uint4*>(
-                      static_cast<const typename C::T*>(ep.bias) + col));
-                  const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+        for (int i = 0; i < H0; ++i) {
+          if (i < ccount) {
+            const int c = cbase + i;
+            tmem_ld_wait();
+            if (i + 1 < ccount) {
+              tmem_ld_x32(taddr + (c + 1) * 32, vbuf[(i + 1) & 1]);
+              load_res(c + 1, rbuf[(i + 1) & 1]);
+            }
+            const uint32_t(&v)[32] = vbuf[i & 1];
+            const uint4(&rr)[4] = rbuf[i & 1];
+            const int col0 = n_tile * BN + c * 32;
+            if (row_ok) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 t = C::unpack(bw[j]);
-                    f[2 * j] += t.x;
-                    f[2 * j + 1] += t.y;
+              for (int q = 0; q < 4; ++q) {
+                const int col = col0 + q * 8;
+                if (col < N) {  // N % 8 == 0
+                  float f[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+                  if (ep.bias) {
+                    const uint4 b = __ldg(reinterpret_cast<const uint4*>(static_cast<const T*>(ep.bias) + col));
+                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 t = C::unpack(bw[j]);
+                      f[2 * j] += t.x;
+                      f[2 * j + 1] += t.y;
+                    }
                   }
-                }
-                if (ep.rowvec) {
-                  const uint4 b = __ldg(reinterpret_cast<const uint4*>(
-                      static_cast<const typename C::T*>(ep.rowvec) + grp * ep.ld_rowvec + col));
-                  const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+                  if (rv) {
+                    const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + col));
+                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 t = C::unpack(bw[j]);
-                    f[2 * j] += t.x;
-                    f[2 * j + 1] += t.y;
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 t = C::unpack(bw[j]);
+                      f[2 * j] += t.x;
+                      f[2 * j + 1] += t.y;
+                    }
                   }
-                }
-                if (ep.residual) {
-                  const uint4 b = *reinterpret_cast<const uint4*>(
-                      static_cast<const typename C::T*>(ep.residual) + row * ep.ld_res + col);
-                  const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+                  if (res) {
+                    const uint32_t bw[4] = {rr[q].x, rr[q].y, rr[q].z, rr[q].w};
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 t = C::unpack(bw[j]);
-                    f[2 * j] += t.x;
-                    f[2 * j + 1] += t.y;
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 t = C::unpack(bw[j]);
+                      f[2 * j] += t.x;
+                      f[2 * j + 1] += t.y;
+                    }
                   }
-                }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  f[j] *= ep.scale;
-                  if (ep.act == MIMO_ACT_SILU) f[j] = silu_f(f[j]);
+                  for (int j = 0; j < 8; ++j) {
+                    f[j] *= ep.scale;
+                    if (ep.act == MIMO_ACT_SILU) f[j] = silu_f(f[j]);
+                  }
+                  uint4 o;
+                  o.x = C::pack(f[0], f[1]);
+                  o.y = C::pack(f[2], f[3]);
+                  o.z = C::pack(f[4], f[5]);
+                  o.w = C::pack(f[6], f[7]);
+                  *reinterpret_cast<uint4*>(outp + col) = o;
                 }
-                uint4 o;
-                o.x = C::pack(f[0], f[1]);
-                o.y = C::pack(f[2], f[3]);
-                o.z = C::pack(f[4], f[5]);
-                o.w = C::pack(f[6], f[7]);
-                *reinterpret_cast<uint4*>(static_cast<typename C::T*>(ep.out) + row * ep.ldo + col) = o;
               }
             }
           }
         }
       } else {
-        // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates.
+        // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates; 32-column pairs are split
+        // between the two warp groups.
         constexpr int HALF = BN / 2;
-        for (int c = 0; c < HALF / 32; ++c) {
-          uint32_t v[32], gt[32];
-          tmem_ld_x32(taddr + c * 32, v);
-          tmem_ld_x32(taddr + HALF + c * 32, gt);
-          tmem_ld_wait();
-          const int pcol0 = n_tile * BN + c * 32;          // packed column of the value half
-          const int ocol0 = n_tile * HALF + c * 32;        // output column
-          if (row_ok) {
+        constexpr int NPAIR = HALF / 32;
+        constexpr int P0 = (NPAIR + 1) / 2;
+        const int pbase = hsel ? P0 : 0;
+        const int pcount = hsel ? NPAIR - P0 : P0;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float fv[8], fg[8];
+        for (int i = 0; i < P0; ++i) {
+          if (i < pcount) {
+            const int c = pbase + i;
+            uint32_t v[32], gt[32];
+            tmem_ld_x32(taddr + c * 32, v);
+            tmem_ld_x32(taddr + HALF + c * 32, gt);
+            tmem_ld_wait();
+            const int pcol0 = n_tile * BN + c * 32;    // packed column of the value half
+            const int ocol0 = n_tile * HALF + c * 32;  // output column
+            if (row_ok) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                fv[j] = __uint_as_float(v[q * 8 + j]);
-                fg[j] = __uint_as_float(gt[q * 8 + j]);
-              }
-              if (ep.bias) {
-                const typename C::T* bp = static_cast<const typename C::T*>(ep.bias);
-                const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(bp + pcol0 + q * 8));
-                const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(bp + pcol0 + HALF + q * 8));
-                const uint32_t w0[4] = {b0.x, b0.y, b0.z, b0.w};
-                const uint32_t w1[4] = {b1.x, b1.y, b1.z, b1.w};
+              for (int q = 0; q < 4; ++q) {
+                float fv[8], fg[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 t0 = C::unpack(w0[j]);
-                  const float2 t1 = C::unpack(w1[j]);
-                  fv[2 * j] += t0.x;
-                  fv[2 * j + 1] += t0.y;
-                  fg[2 * j] += t1.x;
-                  fg[2 * j + 1] += t1.y;
+                for (int j = 0; j < 8; ++j) {
+                  fv[j] = __uint_as_float(v[q * 8 + j]);
+                  fg[j] = __uint_as_float(gt[q * 8 + j]);
                 }
-              }
-              float f[8];
+                if (ep.bias) {
+                  const T* bp = static_cast<const T*>(ep.bias);
+                  const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(bp + pcol0 + q * 8));
+                  const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(bp + pcol0 + HALF + q * 8));
+                  const uint32_t w0[4] = {b0.x, b0.y, b0.z, b0.w};
+                  const uint32_t w1[4] = {b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fv[j] * gelu_erf_f(fg[j]);
-              uint4 o;
-              o.x = C::pack(f[0], f[1]);
-              o.y = C::pack(f[2], f[3]);
-              o.z = C::pack(f[4], f[5]);
-              o.w = C::pack(f[6], f[7]);
-              *reinterpret_cast<uint4*>(static_cast<typename C::T*>(ep.out) + row * ep.ldo + ocol0 + q * 8) = o;
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 t0 = C::unpack(w0[j]);
+                    const float2 t1 = C::unpack(w1[j]);
+                    fv[2 * j] += t0.x;
+                    fv[2 * j + 1] += t0.y;
+                    fg[2 * j] += t1.x;
+                    fg[2 * j + 1] += t1.y;
+                  }
+                }
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fv[j] * gelu_erf_fast(fg[j]);
+                uint4 o;
+                o.x = C::pack(f[0], f[1]);
+                o.y = C::pack(f[2], f[3]);
+                o.z = C::pack(f[4], f[5]);
+                o.w = C::pack(f[6], f[7]);
+                *reinterpret_cast<uint4*>(static_cast<T*>(ep.out) + row * ep.ldo + ocol0 + q * 8) = o;
+              }
             }
           }
         }

@@ -223,6 +223,25 @@ def temporal():
         ref = torch.nn.functional.scaled_dot_product_attention(tr(q), tr(k), tr(v))
         ref = ref.reshape(bsz, hw, heads, f, d).permute(0, 3, 1, 2, 4).reshape(bsz * f * hw, C)
         ok &= report(f"attn_temporal b={bsz} f={f} hw={hw} d={d}", out, ref)
+    # frame-sharded form: this "rank" owns frames [r*fl, (r+1)*fl); K|V of all ranks sit in rank-major chunks
+    for (bsz, f, hw, heads, d, world) in [(2, 24, 8, 8, 40, 2), (2, 24, 4, 8, 80, 4), (1, 24, 4, 8, 160, 8)]:
+        C = heads * d
+        fl = f // world
+        q_full = torch.randn(bsz, f, hw, C, device=DEV).half()
+        kv_full = torch.randn(bsz, f, hw, 2 * C, device=DEV).half()
+        # chunk g holds frames [g*fl, (g+1)*fl) of every batch entry: [(b, f_local, p)] rows
+        kv_chunks = torch.cat([kv_full[:, gg * fl:(gg + 1) * fl].reshape(bsz * fl * hw, 2 * C) for gg in range(world)])
+
+        def tr(t_, ff):
+            return t_.float().reshape(bsz, ff, hw, heads, d).permute(0, 2, 3, 1, 4).reshape(bsz * hw, heads, ff, d)
+
+        for rk in (0, world - 1):
+            q = q_full[:, rk * fl:(rk + 1) * fl].reshape(bsz * fl * hw, C).contiguous()
+            out = ops.attn_temporal(q, kv_chunks[:, :C], kv_chunks[:, C:], bsz, f, hw, heads, q_frames=fl,
+                                    frames_per_chunk=fl, chunk_stride_rows=bsz * fl * hw)
+            ref = torch.nn.functional.scaled_dot_product_attention(tr(q, fl), tr(kv_full[..., :C], f), tr(kv_full[..., C:], f))
+            ref = ref.reshape(bsz, hw, heads, fl, d).permute(0, 3, 1, 2, 4).reshape(bsz * fl * hw, C)
+            ok &= report(f"attn_temporal sharded world={world} rank={rk} d={d}", out, ref)
     return ok
 
 

@@ -20,7 +20,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    from tests.test_engine_gpu import _pil_inputs
+    import numpy as np
+    import PIL.Image
+
+    def _pil_inputs(F_, size, seed):
+        rng = np.random.RandomState(seed)
+        ref_img = PIL.Image.fromarray(rng.randint(0, 256, (size, size, 3), dtype=np.uint8))
+        poses, bks = [], []
+        for i in range(F_):
+            a = np.zeros((size, size, 3), np.uint8)
+            a[size // 4: size // 2 + i % 8, size // 3: size // 3 + 20] = rng.randint(11, 256, 3)
+            poses.append(PIL.Image.fromarray(a))
+            bks.append(PIL.Image.fromarray(rng.randint(0, 256, (size, size, 3), dtype=np.uint8)))
+        return ref_img, poses, bks
+
     from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
 
     from mimo_b200.host import modules as M
