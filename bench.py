@@ -198,10 +198,21 @@ def run_ours(args):
     assert res.videos.shape == (1, 3, FRAMES, HEIGHT, WIDTH)
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (one extra, untimed clip with event brackets) ----
+    # The brackets must time kernels, not the host: each forward is preceded by a ~40 ms device-side spin so that the
+    # host runs ahead and the ~1 400 launches of the forward sit back to back in the stream when they execute.
+    den_eng = pipe.denoising_unet.engine()
+    orig_impl = den_eng._forward_impl
+
+    def queued_impl(*a):
+        torch.cuda._sleep(80_000_000)
+        return orig_impl(*a)
+
+    den_eng._forward_impl = queued_impl
     ops.PROFILE = []
     pipe.sample_tensors(dev_in, DDIM_STEPS, GUIDANCE)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
+    den_eng._forward_impl = orig_impl
     agg = {}
     for name, fl, by, a, b in prof:
         d = agg.setdefault(name, [0.0, 0.0, 0.0, 0])

@@ -178,23 +178,32 @@ class UNetEngine:
             bs.append(b)
         W["temb_all"] = (torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous())
         self.clip_state: Optional[dict] = None
+        self._persist: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._graphs: Dict[tuple, dict] = {}
+        self.use_graphs = True
+        self._launches_per_forward = 0
 
     # ------------------------------------------------------------------------------------------------
-    def _time_embed(self, timesteps: torch.Tensor) -> torch.Tensor:
-        """Timesteps(flip_sin_to_cos, shift 0) on the host in fp32 (unet_3d_edit_bkfill.py:462-467), then the
-        TimestepEmbedding MLP and ALL resnets' time_emb_proj(silu(emb)) as three GEMMs. -> [b, sum(Cout)]"""
+    def _sinusoid(self, timesteps: torch.Tensor) -> torch.Tensor:
+        """Timesteps(flip_sin_to_cos, shift 0) in fp32, cast to the model dtype (unet_3d_edit_bkfill.py:462-467)."""
         c0 = self.spec.block_out_channels[0]
         half = c0 // 2
         t = timesteps.to(device=self.device, dtype=torch.float32).reshape(-1)
         exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=self.device) / half
         emb = t[:, None] * torch.exp(exponent)[None, :]
-        emb = torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1).to(self.dtype).contiguous()
+        return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1).to(self.dtype).contiguous()
+
+    def _time_embed_from(self, emb: torch.Tensor) -> torch.Tensor:
+        """TimestepEmbedding MLP and ALL resnets' time_emb_proj(silu(emb)) as three GEMMs. -> [b, sum(Cout)]"""
         w1, b1 = self.w["time1"]
         w2, b2 = self.w["time2"]
         h = ops.gemm(emb, w1, bias=b1, act=L.ACT_SILU)
         h = ops.gemm(h, w2, bias=b2, act=L.ACT_SILU)  # only silu(emb) is ever consumed (resnet.py:226)
         wa, ba = self.w["temb_all"]
         return ops.gemm(h, wa, bias=ba)
+
+    def _time_embed(self, timesteps: torch.Tensor) -> torch.Tensor:
+        return self._time_embed_from(self._sinusoid(timesteps))
 
     def _resnet(self, p, x0, x1, tembs, n, h, w, rows_per_branch):
         r = self.w[p]
@@ -368,29 +377,42 @@ class UNetEngine:
         self._body(x, tembs, nbr, 1, h, w, xf_write, stop_at=last)
         return banks
 
+    # ------------------------------------------------------------------------------------------------
+    # per-clip state lives in PERSISTENT buffers (same addresses for every clip) so that captured CUDA graphs of the
+    # forward stay valid: begin_clip / set_cross_attn copy new values in place.
+    def _store(self, slot: str, new: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        cur = self._persist.get(slot)
+        if cur is not None and cur.keys() == new.keys() and all(cur[k].shape == new[k].shape for k in new):
+            for k in new:
+                cur[k].copy_(new[k])
+            return cur
+        self._persist[slot] = new
+        self._graphs.clear()  # addresses changed: captured graphs are stale
+        return new
+
+    def set_cross_attn(self, ehs: torch.Tensor):
+        self.clip_state["xattn"] = self._store("xattn", self.cross_attn_vectors(ehs))
+
     def begin_clip(self, ehs: torch.Tensor, banks: Dict[str, torch.Tensor], cfg: bool, frames: int):
         """Per-clip state of the denoising UNet: folded cross-attention vectors, projected banks, bank routing."""
-        b = ehs.shape[0]
-        if cfg:
-            idx = [-1] * frames + [1] * frames  # unconditional rows ignore the bank (mutual_self_attention.py:177-197)
-        else:
-            idx = [0] * (b * frames)
-        self.clip_state = {
-            "xattn": self.cross_attn_vectors(ehs), "banks": banks,
-            "bank_index": torch.tensor(idx, dtype=torch.int32, device=self.device), "frames": frames, "cfg": cfg,
-        }
+        self.clip_state = {"banks": self._store("banks", banks), "cfg": cfg, "frames": 0, "batch": ehs.shape[0],
+                           "bank_index": None}
+        self.set_cross_attn(ehs)
+        self.begin_clip_frames(frames, ehs.shape[0])
 
-    def forward(self, sample: torch.Tensor, timestep, pose_nhwc: Optional[torch.Tensor]) -> torch.Tensor:
-        """UNet3DConditionModel.forward (unet_3d_edit_bkfill.py:398-576). sample [b, 8, f, h, w] (reference layout,
-        any float dtype); pose_nhwc [(b f) h w, 320] channels-last or None. Returns [b, 4, f, h, w]."""
+    def begin_clip_frames(self, frames: int, b: int):
         st = self.clip_state
-        assert st is not None, "begin_clip() must run before forward()"
+        idx = ([-1] * frames + [1] * frames) if st["cfg"] else [0] * (b * frames)
+        # unconditional rows ignore the bank (mutual_self_attention.py:177-197)
+        new = torch.tensor(idx, dtype=torch.int32, device=self.device)
+        st["bank_index"] = self._store(f"bank_index_{len(idx)}", {"i": new})["i"]
+        st["frames"] = frames
+
+    def _forward_impl(self, sample: torch.Tensor, emb: torch.Tensor, pose_nhwc: Optional[torch.Tensor]) -> torch.Tensor:
+        st = self.clip_state
         b, c, f, h, w = sample.shape
-        if st["bank_index"].numel() != b * f:
-            self.begin_clip_frames(f, b)
-        x_in = ops.ncfhw_to_nhwc(sample.contiguous(), (c + 7) // 8 * 8, self.dtype)
-        t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep])
-        tembs = self._time_embed(t.reshape(-1).expand(b) if t.numel() == 1 else t)
+        x_in = ops.ncfhw_to_nhwc(sample, (c + 7) // 8 * 8, self.dtype)
+        tembs = self._time_embed_from(emb)
         wci, bci = self.w["conv_in"]
         x = ops.conv3x3(x_in, wci, b * f, h, w, bias=bci, residual=pose_nhwc)
         xf = lambda p, xx, n, hw, rpb: self._xf_read(p, xx, n, hw, rpb, st)
@@ -401,12 +423,53 @@ class UNetEngine:
         y = ops.conv3x3(x, wco, b * f, h, w, bias=bco)
         return ops.nhwc_to_ncfhw(y, b, self.spec.out_channels, f, h, w)
 
-    def begin_clip_frames(self, frames: int, b: int):
+    def forward(self, sample: torch.Tensor, timestep, pose_nhwc: Optional[torch.Tensor]) -> torch.Tensor:
+        """UNet3DConditionModel.forward (unet_3d_edit_bkfill.py:398-576). sample [b, 8, f, h, w] (reference layout,
+        any float dtype); pose_nhwc [(b f) h w, 320] channels-last or None. Returns [b, 4, f, h, w].
+        The ~1 400 kernel launches of one forward are a fixed graph per input shape: after one eager run they are
+        captured into a CUDA graph and replayed (the returned tensor is then a static buffer, valid until the next
+        forward of the same shape)."""
         st = self.clip_state
-        cfg = st["cfg"]
-        idx = ([-1] * frames + [1] * frames) if cfg else [0] * (b * frames)
-        st["bank_index"] = torch.tensor(idx, dtype=torch.int32, device=self.device)
-        st["frames"] = frames
+        assert st is not None, "begin_clip() must run before forward()"
+        b, c, f, h, w = sample.shape
+        if st["bank_index"] is None or st["bank_index"].numel() != b * f:
+            self.begin_clip_frames(f, b)
+        t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep])
+        emb = self._sinusoid(t.reshape(-1).expand(b) if t.numel() == 1 else t)
+        sample = sample.contiguous()
+        if not self.use_graphs or self.taps is not None or ops.PROFILE is not None or self.shard[1] > 1:
+            return self._forward_impl(sample, emb, pose_nhwc)
+        key = (tuple(sample.shape), sample.dtype, pose_nhwc is not None, st["bank_index"].data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            g = {"calls": 0}
+            self._graphs[key] = g
+        if "graph" not in g:
+            g["calls"] += 1
+            if g["calls"] < 2:  # first call of a shape runs eagerly (lazy one-time setup inside the C library)
+                return self._forward_impl(sample, emb, pose_nhwc)
+            g["sample"] = sample.clone()
+            g["emb"] = emb.clone()
+            g["pose"] = pose_nhwc.clone() if pose_nhwc is not None else None
+            g["pose_src"] = None
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            l0 = ops.launches()
+            with torch.cuda.graph(graph):
+                g["out"] = self._forward_impl(g["sample"], g["emb"], g["pose"])
+            g["graph"] = graph
+            g["launches"] = ops.launches() - l0  # kernels recorded in the graph (nothing ran during capture)
+            ops.add_launches(-g["launches"])
+        g["sample"].copy_(sample)
+        g["emb"].copy_(emb)
+        if pose_nhwc is not None:
+            src = (pose_nhwc.data_ptr(), pose_nhwc._version)
+            if g["pose_src"] != src:  # the window's pose features change once per clip, not per step
+                g["pose"].copy_(pose_nhwc)
+                g["pose_src"] = src
+        g["graph"].replay()
+        ops.add_launches(g["launches"])
+        return g["out"]
 
 
 class PoseGuiderEngine:

@@ -308,7 +308,7 @@ class UNet3DConditionModel(_UNetBase):
         b, c, f, h, w = sample.shape
         key = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, tuple(encoder_hidden_states.shape))
         if key != self._xattn_key:
-            eng.clip_state["xattn"] = eng.cross_attn_vectors(encoder_hidden_states)
+            eng.set_cross_attn(encoder_hidden_states)
             self._xattn_key = key
         pose = None
         if pose_cond_fea is not None:

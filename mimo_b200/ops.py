@@ -23,6 +23,12 @@ def launches() -> int:
     return _launches
 
 
+def add_launches(k: int) -> None:
+    """Account for kernels launched by a CUDA-graph replay (the graph was recorded from these same wrappers)."""
+    global _launches
+    _launches += k
+
+
 class _Call:
     """Counts kernel launches and, when profiling, brackets the call with events."""
 
