@@ -213,6 +213,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     den_eng._forward_impl = orig_impl
+    if args.dump_calls and rank == 0:
+        with open(args.dump_calls, "w") as fcsv:
+            fcsv.write("idx,name,flops,bytes,ms\n")
+            for i, (name, fl, by, a, b) in enumerate(prof):
+                fcsv.write(f"{i},{name},{fl:.0f},{by:.0f},{a.elapsed_time(b):.4f}\n")
     agg = {}
     for name, fl, by, a, b in prof:
         d = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
@@ -238,7 +243,7 @@ def run_ours(args):
 
     if rank != 0:
         return
-    cpu = cpu_baseline_sample()
+    cpu = None if args.no_cpu_baseline else cpu_baseline_sample()
     line = {
         "metric": METRIC, "value": round(value, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "strong",
@@ -327,6 +332,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dump-calls", default=None, help="write every profiled C-ABI call (name, flops, bytes, ms) as CSV")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU sample (development runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps, args.warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
