@@ -56,7 +56,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 160 ? 5 : (BN >= 128 ? 6 : 8));
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*sbias*/;
 };
 
 template <int BN, bool kBf16>
@@ -74,6 +74,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>(bars + 32);  // [2][256] per-tile column constants (after 256 B of barriers)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,45 +209,70 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 
+      // ---- per-tile column constants -> smem: bias (+ the per-branch vector when the whole tile shares one group) ----
+      long long grp_first, grp_last;
+      if (!g.conv) {
+        const long long m0 = static_cast<long long>(m_tile) * BM;
+        long long m1 = m0 + BM - 1;
+        if (m1 > M - 1) m1 = M - 1;
+        grp_first = m0 / ep.rows_per_group;
+        grp_last = m1 / ep.rows_per_group;
+      } else {
+        const int x0 = (m_tile % g.tiles_w) * g.TW;
+        const int y0 = ((m_tile / g.tiles_w) % g.tiles_h) * g.TH;
+        const int n0 = (m_tile / (g.tiles_w * g.tiles_h)) * g.TN;
+        int n1 = n0 + g.TN - 1;
+        if (n1 > g.NI - 1) n1 = g.NI - 1;
+        grp_first = (static_cast<long long>(n0) * g.H * g.W) / ep.rows_per_group;
+        grp_last = (static_cast<long long>(n1 + 1) * g.H * g.W - 1) / ep.rows_per_group;
+        (void)x0;
+        (void)y0;
+      }
+      const bool rv_uniform = ep.rowvec != nullptr && grp_first == grp_last;
+      float* sb = sbias + acc * 256;
+      {
+        const int e = (warp - 4) * 32 + lane;
+        for (int j = e; j < BN; j += 256) {
+          const int col = n_tile * BN + j;
+          float v = 0.f;
+          if (col < N) {
+            if (ep.bias) v = C::to_f(static_cast<const T*>(ep.bias)[col]);
+            if (rv_uniform) v += C::to_f(static_cast<const T*>(ep.rowvec)[grp_first * ep.ld_rowvec + col]);
+          }
+          sb[j] = v;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+      const T* rv = (ep.rowvec && !rv_uniform && row_ok)
+                        ? static_cast<const T*>(ep.rowvec) + (row / ep.rows_per_group) * ep.ld_rowvec
+                        : nullptr;
+
       if (ep.act != MIMO_ACT_GEGLU) {
         const int cbase = hsel ? H0 : 0;
         const int ccount = hsel ? NCHUNK - H0 : H0;
-        const long long grp = ep.rowvec ? row / ep.rows_per_group : 0;
-        const T* rv = ep.rowvec ? static_cast<const T*>(ep.rowvec) + grp * ep.ld_rowvec : nullptr;
         const T* res = (ep.residual && row_ok) ? static_cast<const T*>(ep.residual) + row * ep.ld_res : nullptr;
         T* outp = static_cast<T*>(ep.out) + row * ep.ldo;
-        uint4 rbuf[2][4];
-        uint32_t vbuf[2][32];
-        auto load_res = [&](int c, uint4 (&dst)[4]) {
-          const int col0 = n_tile * BN + c * 32;
+        // the whole residual row segment of this thread is requested BEFORE the accumulator is awaited: the loads
+        // fly while the tensor pipe still works on this tile
+        uint4 rbuf[H0][4];
+#pragma unroll
+        for (int i = 0; i < H0; ++i) {
+          const int col0 = n_tile * BN + (cbase + i) * 32;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            dst[q] = make_uint4(0, 0, 0, 0);
-            if (res && col0 + q * 8 < N) dst[q] = *reinterpret_cast<const uint4*>(res + col0 + q * 8);
+            rbuf[i][q] = make_uint4(0, 0, 0, 0);
+            if (res && i < ccount && col0 + q * 8 < N) rbuf[i][q] = *reinterpret_cast<const uint4*>(res + col0 + q * 8);
           }
-        };
-        if (res) {  // pull the rest of this thread's residual row segment towards L2 while the main loop still runs
-          const int c_lo = n_tile * BN + cbase * 32;
-          int c_hi = c_lo + ccount * 32;
-          if (c_hi > N) c_hi = N;
-          for (int cc = c_lo + 64; cc < c_hi; cc += 64)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(res + cc));
         }
-        if (ccount > 0) load_res(cbase, rbuf[0]);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        if (ccount > 0) tmem_ld_x32(taddr + cbase * 32, vbuf[0]);
 #pragma unroll
         for (int i = 0; i < H0; ++i) {
           if (i < ccount) {
             const int c = cbase + i;
+            uint32_t v[32];
+            tmem_ld_x32(taddr + c * 32, v);
             tmem_ld_wait();
-            if (i + 1 < ccount) {
-              tmem_ld_x32(taddr + (c + 1) * 32, vbuf[(i + 1) & 1]);
-              load_res(c + 1, rbuf[(i + 1) & 1]);
-            }
-            const uint32_t(&v)[32] = vbuf[i & 1];
-            const uint4(&rr)[4] = rbuf[i & 1];
             const int col0 = n_tile * BN + c * 32;
             if (row_ok) {
 #pragma unroll
@@ -254,18 +280,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 const int col = col0 + q * 8;
                 if (col < N) {  // N % 8 == 0
                   float f[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
-                  if (ep.bias) {
-                    const uint4 b = __ldg(reinterpret_cast<const uint4*>(static_cast<const T*>(ep.bias) + col));
-                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const float2 t = C::unpack(bw[j]);
-                      f[2 * j] += t.x;
-                      f[2 * j + 1] += t.y;
-                    }
-                  }
+                  const float4 b0 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8);
+                  const float4 b1 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8 + 4);
+                  f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x;
+                  f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
+                  f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z;
+                  f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
+                  f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x;
+                  f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
+                  f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z;
+                  f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
                   if (rv) {
                     const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + col));
                     const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
@@ -277,7 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     }
                   }
                   if (res) {
-                    const uint32_t bw[4] = {rr[q].x, rr[q].y, rr[q].z, rr[q].w};
+                    const uint32_t bw[4] = {rbuf[i][q].x, rbuf[i][q].y, rbuf[i][q].z, rbuf[i][q].w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                       const float2 t = C::unpack(bw[j]);
@@ -319,36 +343,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             tmem_ld_x32(taddr + c * 32, v);
             tmem_ld_x32(taddr + HALF + c * 32, gt);
             tmem_ld_wait();
-            const int pcol0 = n_tile * BN + c * 32;    // packed column of the value half
             const int ocol0 = n_tile * HALF + c * 32;  // output column
             if (row_ok) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                float fv[8], fg[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  fv[j] = __uint_as_float(v[q * 8 + j]);
-                  fg[j] = __uint_as_float(gt[q * 8 + j]);
-                }
-                if (ep.bias) {
-                  const T* bp = static_cast<const T*>(ep.bias);
-                  const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(bp + pcol0 + q * 8));
-                  const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(bp + pcol0 + HALF + q * 8));
-                  const uint32_t w0[4] = {b0.x, b0.y, b0.z, b0.w};
-                  const uint32_t w1[4] = {b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 t0 = C::unpack(w0[j]);
-                    const float2 t1 = C::unpack(w1[j]);
-                    fv[2 * j] += t0.x;
-                    fv[2 * j + 1] += t0.y;
-                    fg[2 * j] += t1.x;
-                    fg[2 * j + 1] += t1.y;
-                  }
-                }
                 float f[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fv[j] * gelu_erf_fast(fg[j]);
+                for (int j = 0; j < 8; ++j) {
+                  const float fv = __uint_as_float(v[q * 8 + j]) + sb[c * 32 + q * 8 + j];
+                  const float fg = __uint_as_float(gt[q * 8 + j]) + sb[HALF + c * 32 + q * 8 + j];
+                  f[j] = fv * gelu_erf_fast(fg);
+                }
                 uint4 o;
                 o.x = C::pack(f[0], f[1]);
                 o.y = C::pack(f[2], f[3]);
