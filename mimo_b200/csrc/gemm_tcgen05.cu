@@ -51,20 +51,30 @@ struct ConvGeom {
   int a_bytes;    // bytes one A box deposits in shared memory
 };
 
-template <int BN>
+// kRes: the epilogue adds a residual tensor. Its rows are pulled into shared memory with cp.async by the very thread
+// that will consume them, kResDepth tiles ahead of the accumulator they belong to, so the residual's DRAM latency is
+// never on the tile-to-tile critical path (each thread only reads back what it copied: no extra barrier).
+template <int BN, bool kRes>
 struct GemmCfg {
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 160 ? 5 : (BN >= 128 ? 6 : 8));
+  static constexpr int kResDepth = kRes ? (BN >= 256 ? 1 : 2) : 0;
+  static constexpr int kResPitch = BN * 2 + 16;  // bytes per row slot (+16: 16-byte reads of 32 rows hit distinct banks)
+  static constexpr int kResBytes = kResDepth * BM * kResPitch;
+  static constexpr int kFixed = 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*sbias*/ + kResBytes;
+  static constexpr int kMaxStages = (BN >= 256) ? 4 : (BN >= 160 ? 5 : (BN >= 128 ? 6 : 8));
+  static constexpr int kFit = (227 * 1024 - kFixed) / kStageBytes;
+  static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*sbias*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
+  static_assert(kStages >= 2, "pipeline too shallow");
 };
 
-template <int BN, bool kBf16>
+template <int BN, bool kBf16, bool kRes>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, int M, int N, int num_m_tiles, int num_n_tiles,
                     int num_k_blocks, ConvGeom g, EpiArgs ep) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kRes>;
   using C = Cvt<kBf16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -75,6 +85,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* sbias = reinterpret_cast<float*>(bars + 32);  // [2][256] per-tile column constants (after 256 B of barriers)
+  uint8_t* sres = reinterpret_cast<uint8_t*>(sbias + 512);  // [kResDepth][128 rows][kResPitch] residual row slots
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -187,6 +198,53 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     constexpr int NCHUNK = BN / 32;
     constexpr int H0 = (NCHUNK + 1) / 2;
     using T = typename C::T;
+    auto tile_row = [&](int tile_, long long& row_, bool& ok_) {
+      const int m_tile_ = tile_ / num_n_tiles;
+      if (!g.conv) {
+        row_ = static_cast<long long>(m_tile_) * BM + r;
+        ok_ = row_ < M;
+      } else {
+        const int x0 = (m_tile_ % g.tiles_w) * g.TW;
+        const int y0 = ((m_tile_ / g.tiles_w) % g.tiles_h) * g.TH;
+        const int n0 = (m_tile_ / (g.tiles_w * g.tiles_h)) * g.TN;
+        const int x = r % g.TW, y = (r / g.TW) % g.TH, n = r / (g.TW * g.TH);
+        ok_ = (n < g.TN) && (x0 + x < g.W) && (y0 + y < g.H) && (n0 + n < g.NI);
+        row_ = (static_cast<long long>(n0 + n) * g.H + (y0 + y)) * g.W + (x0 + x);
+      }
+    };
+    const int cbase_ = hsel ? H0 : 0;
+    const int ccount_ = hsel ? NCHUNK - H0 : H0;
+    // residual prefetch (kRes): this thread's row segment of tile `tile_` -> its slot in ring entry `slot`
+    auto prefetch_res = [&](int tile_, int slot) {
+      if constexpr (kRes) {
+        if (tile_ < num_tiles) {
+          long long row_;
+          bool ok_;
+          tile_row(tile_, row_, ok_);
+          if (ok_) {
+            const int n_tile_ = tile_ % num_n_tiles;
+            const T* src = static_cast<const T*>(ep.residual) + row_ * ep.ld_res + n_tile_ * BN;
+            const uint32_t dst = smem_u32(sres + (slot * BM + r) * Cfg::kResPitch);
+#pragma unroll
+            for (int i = 0; i < H0; ++i) {
+              if (i < ccount_) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int cc = (cbase_ + i) * 32 + q * 8;
+                  if (n_tile_ * BN + cc < N)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + cc * 2), "l"(src + cc) : "memory");
+                }
+              }
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    };
+    if constexpr (kRes) {
+#pragma unroll
+      for (int dd = 0; dd < Cfg::kResDepth; ++dd) prefetch_res(blockIdx.x + dd * gridDim.x, dd);
+    }
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int m_tile = tile / num_n_tiles;
@@ -196,17 +254,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
       long long row;
       bool row_ok;
-      if (!g.conv) {
-        row = static_cast<long long>(m_tile) * BM + r;
-        row_ok = row < M;
-      } else {
-        const int x0 = (m_tile % g.tiles_w) * g.TW;
-        const int y0 = ((m_tile / g.tiles_w) % g.tiles_h) * g.TH;
-        const int n0 = (m_tile / (g.tiles_w * g.tiles_h)) * g.TN;
-        const int x = r % g.TW, y = (r / g.TW) % g.TH, n = r / (g.TW * g.TH);
-        row_ok = (n < g.TN) && (x0 + x < g.W) && (y0 + y < g.H) && (n0 + n < g.NI);
-        row = (static_cast<long long>(n0 + n) * g.H + (y0 + y)) * g.W + (x0 + x);
-      }
+      tile_row(tile, row, row_ok);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 
       // ---- per-tile column constants -> smem: bias (+ the per-branch vector when the whole tile shares one group) ----
@@ -250,22 +298,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       if (ep.act != MIMO_ACT_GEGLU) {
         const int cbase = hsel ? H0 : 0;
         const int ccount = hsel ? NCHUNK - H0 : H0;
-        const T* res = (ep.residual && row_ok) ? static_cast<const T*>(ep.residual) + row * ep.ld_res : nullptr;
+        const bool res = kRes && row_ok;
         T* outp = static_cast<T*>(ep.out) + row * ep.ldo;
-        // the whole residual row segment of this thread is requested BEFORE the accumulator is awaited: the loads
-        // fly while the tensor pipe still works on this tile
-        uint4 rbuf[H0][4];
-#pragma unroll
-        for (int i = 0; i < H0; ++i) {
-          const int col0 = n_tile * BN + (cbase + i) * 32;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            rbuf[i][q] = make_uint4(0, 0, 0, 0);
-            if (res && i < ccount && col0 + q * 8 < N) rbuf[i][q] = *reinterpret_cast<const uint4*>(res + col0 + q * 8);
-          }
-        }
+        constexpr int RD = Cfg::kResDepth > 0 ? Cfg::kResDepth : 1;
+        const uint8_t* rslot = sres + ((lt % RD) * BM + r) * Cfg::kResPitch;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
+        if constexpr (kRes) {  // this tile's residual rows have landed (later tiles' copies may still be in flight)
+          if constexpr (Cfg::kResDepth == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
 #pragma unroll
         for (int i = 0; i < H0; ++i) {
           if (i < ccount) {
@@ -301,7 +343,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     }
                   }
                   if (res) {
-                    const uint32_t bw[4] = {rbuf[i][q].x, rbuf[i][q].y, rbuf[i][q].z, rbuf[i][q].w};
+                    const uint4 rr = *reinterpret_cast<const uint4*>(rslot + (c * 32 + q * 8) * 2);
+                    const uint32_t bw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                       const float2 t = C::unpack(bw[j]);
@@ -325,6 +368,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             }
           }
         }
+        if constexpr (kRes) prefetch_res(tile + Cfg::kResDepth * static_cast<int>(gridDim.x), lt % RD);
       } else {
         // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates; 32-column pairs are split
         // between the two warp groups.
@@ -370,6 +414,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if constexpr (kRes) asm volatile("cp.async.wait_all;" ::: "memory");
   }
 
   tc_fence_before();
@@ -383,11 +428,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, bool kBf16>
+template <int BN, bool kBf16, bool kRes>
 static int launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, int M, int N, int mt,
                       int nt, int nkb, const ConvGeom& g, const EpiArgs& ep, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, kBf16>;
+  using Cfg = GemmCfg<BN, kRes>;
+  auto kern = gemm_tcgen05_kernel<BN, kBf16, kRes>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -405,11 +450,20 @@ static int launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
 template <bool kBf16>
 static int launch_bn(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, int M, int N,
                      int mt, int nt, int nkb, const ConvGeom& g, const EpiArgs& ep, cudaStream_t st) {
+  const bool res = ep.residual != nullptr && ep.act != MIMO_ACT_GEGLU;
   switch (bn) {
-    case 64: return launch_cfg<64, kBf16>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
-    case 128: return launch_cfg<128, kBf16>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
-    case 160: return launch_cfg<160, kBf16>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
-    case 256: return launch_cfg<256, kBf16>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+    case 64:
+      return res ? launch_cfg<64, kBf16, true>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st)
+                 : launch_cfg<64, kBf16, false>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+    case 128:
+      return res ? launch_cfg<128, kBf16, true>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st)
+                 : launch_cfg<128, kBf16, false>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+    case 160:
+      return res ? launch_cfg<160, kBf16, true>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st)
+                 : launch_cfg<160, kBf16, false>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+    case 256:
+      return res ? launch_cfg<256, kBf16, true>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st)
+                 : launch_cfg<256, kBf16, false>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
   }
   return set_error(MIMO_ERR_ARG, "gemm: unsupported BN");
 }
