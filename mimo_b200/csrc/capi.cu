@@ -49,7 +49,7 @@ int num_sms() { return g_num_sms; }
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 int encode_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box) {
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -71,7 +71,9 @@ int encode_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const u
   const CUtensorMapDataType dt =
       dtype == MIMO_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = g_encode(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                            : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err),

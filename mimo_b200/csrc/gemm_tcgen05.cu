@@ -3,17 +3,21 @@
 //   D[M,N] = epilogue( A[M,K] . W[N,K]^T )          fp16/bf16 operands, fp32 accumulate in TMEM
 //
 // One CTA per SM loops over 128 x BN output tiles (static round-robin schedule, n-tile fastest so that CTAs
-// running concurrently share A tiles in L2). Roles (256 threads):
-//   warp 0 lane 0 : TMA producer  - fills a ring of {A 128x64, W BNx64} 128B-swizzled stages
-//   warp 1 lane 0 : MMA issuer    - tcgen05.mma.cta_group::1.kind::f16 128xBNx16, accumulators double-buffered
-//                                   in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
+// running concurrently share A tiles in L2). Every byte that crosses the SM boundary moves by TMA; no thread issues
+// a scattered global load or store on the steady-state path. Roles (384 threads):
+//   warp 0 lane 0 : TMA producer   - ring of {A 128x64, W BNx64} 128B-swizzled stages
+//   warp 1 lane 0 : MMA issuer     - tcgen05.mma.cta_group::1.kind::f16 128xBNx16; accumulators double-buffered in
+//                                    TMEM so the epilogue of tile i overlaps the main loop of tile i+1
 //   warp 2        : TMEM allocator
-//   warps 4..11   : epilogue      - tcgen05.ld 32 lanes x 32 columns (two warp groups split the columns), software
-//                                   pipelined with the residual loads; fused bias / per-frame vector / residual /
-//                                   scale / SiLU / GEGLU, 16-byte vector stores
+//   warp 3 lane 0 : residual producer (kRes) - TMA boxes of the residual tensor, 128 rows x 32 columns each, into a
+//                                    ring of 8 KiB slots that runs ahead of the epilogue
+//   warps 4..11   : epilogue       - two groups of 4 warps split the tile's 32-column chunks. Per chunk: tcgen05.ld
+//                                    32 lanes x 32 columns -> + bias / per-branch vector (smem) + residual (smem ring)
+//                                    -> scale / SiLU / GEGLU -> 64B-swizzled staging buffer -> TMA store
 // Convolution mode replaces the A loads by 4-D TMA boxes {64 ch, TW, TH, TN} over the NHWC input, one box per
 // (tap, 64-channel block, source tensor); TMA's out-of-bounds zero fill is the conv's zero padding and also
-// the K tail. Two source tensors give the up-blocks' channel concat without materialising it.
+// the K tail, and the output / residual boxes use the same {TW, TH, TN} footprint (stores are clipped at image
+// borders). Two source tensors give the up-blocks' channel concat without materialising it.
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 
@@ -26,16 +30,13 @@ namespace mimo {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kGemmThreads = 384;
+constexpr int kChunk = 8192;  // one 128-row x 32-column (64 B) epilogue chunk
 
 struct EpiArgs {
   const void* bias;
   const void* rowvec;
-  const void* residual;
-  void* out;
   long long rows_per_group;
   long long ld_rowvec;
-  long long ld_res;
-  long long ldo;
   float scale;
   int act;
 };
@@ -45,47 +46,52 @@ struct ConvGeom {
   int H, W, NI;
   int TW, TH, TN;
   int tiles_w, tiles_h;
-  int ctot;       // c0 + c1
-  int c0;         // channels of source 0
-  int kb0, kb1;   // 64-channel blocks per tap for source 0 / 1
-  int a_bytes;    // bytes one A box deposits in shared memory
+  int ctot;         // c0 + c1
+  int c0;           // channels of source 0 (GEMM mode: K of source 0)
+  int kb0, kb1;     // 64-wide K blocks (per tap in conv mode) of source 0 / 1
+  int a_bytes;      // bytes one A box deposits in shared memory
+  int chunk_bytes;  // bytes one output / residual box moves (TW*TH*TN rows x 64 B)
 };
 
-// kRes: the epilogue adds a residual tensor. Its rows are pulled into shared memory with cp.async by the very thread
-// that will consume them, kResDepth tiles ahead of the accumulator they belong to, so the residual's DRAM latency is
-// never on the tile-to-tile critical path (each thread only reads back what it copied: no extra barrier).
 template <int BN, bool kRes>
 struct GemmCfg {
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
-  static constexpr int kResDepth = kRes ? (BN >= 256 ? 1 : 2) : 0;
-  static constexpr int kResPitch = BN * 2 + 16;  // bytes per row slot (+16: 16-byte reads of 32 rows hit distinct banks)
-  static constexpr int kResBytes = kResDepth * BM * kResPitch;
-  static constexpr int kFixed = 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*sbias*/ + kResBytes;
+  static constexpr int kNChunk = BN / 32;
+  static constexpr int kOutBytes = 2 * 2 * kChunk;  // two warp groups x double buffer
+  static constexpr int kResSlots = kRes ? (BN >= 256 ? 4 : (2 * kNChunk < 8 ? 2 * kNChunk : 8)) : 0;
+  static constexpr int kResBytes = kResSlots * kChunk;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kFixed = kBarBytes + 2048 /*sbias*/ + kOutBytes + kResBytes;
   static constexpr int kMaxStages = (BN >= 256) ? 4 : (BN >= 160 ? 5 : (BN >= 128 ? 6 : 8));
   static constexpr int kFit = (227 * 1024 - kFixed) / kStageBytes;
   static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
-  static_assert(kStages >= 2, "pipeline too shallow");
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
 template <int BN, bool kBf16, bool kRes>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                    const __grid_constant__ CUtensorMap tmB, int M, int N, int num_m_tiles, int num_n_tiles,
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                    const __grid_constant__ CUtensorMap tmRes, int M, int N, int num_m_tiles, int num_n_tiles,
                     int num_k_blocks, ConvGeom g, EpiArgs ep) {
   using Cfg = GemmCfg<BN, kRes>;
   using C = Cvt<kBf16>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + Cfg::kStages;
-  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* sbias = reinterpret_cast<float*>(bars + 32);  // [2][256] per-tile column constants (after 256 B of barriers)
-  uint8_t* sres = reinterpret_cast<uint8_t*>(sbias + 512);  // [kResDepth][128 rows][kResPitch] residual row slots
+  using T = typename C::T;
+  constexpr int NCHUNK = Cfg::kNChunk;
+  extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
+  uint8_t* sOut = smem + Cfg::kStages * Cfg::kStageBytes;  // [2 groups][2 buffers][8 KiB]
+  uint8_t* sRes = sOut + Cfg::kOutBytes;                    // [kResSlots][8 KiB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRes + Cfg::kResBytes);
+  uint64_t* full_bar = bars;         // kStages (<= 8)
+  uint64_t* empty_bar = bars + 8;    // kStages
+  uint64_t* tmem_full = bars + 16;   // 2
+  uint64_t* tmem_empty = bars + 18;  // 2
+  uint64_t* res_full = bars + 20;    // kResSlots (<= 8)
+  uint64_t* res_empty = bars + 28;   // kResSlots
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::kBarBytes);  // [2][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,6 +101,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    if (kRes) tma_prefetch_desc(&tmRes);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -105,6 +113,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 8);
     }
+    for (int s = 0; s < Cfg::kResSlots; ++s) {
+      mbar_init(&res_full[s], 1);
+      mbar_init(&res_empty[s], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -113,19 +125,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile -> coordinates of its first output row / pixel
+  auto tile_origin = [&](int m_tile, int& x0, int& y0, int& n0) {
+    if (g.conv) {
+      x0 = (m_tile % g.tiles_w) * g.TW;
+      y0 = ((m_tile / g.tiles_w) % g.tiles_h) * g.TH;
+      n0 = (m_tile / (g.tiles_w * g.tiles_h)) * g.TN;
+    } else {
+      x0 = y0 = n0 = 0;
+    }
+  };
+
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (operands) =====================
     uint32_t it = 0;
     const int kb_per_tap = g.kb0 + g.kb1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / num_n_tiles;
       const int n_tile = tile % num_n_tiles;
-      int x0 = 0, y0 = 0, n0 = 0;
-      if (g.conv) {
-        x0 = (m_tile % g.tiles_w) * g.TW;
-        y0 = ((m_tile / g.tiles_w) % g.tiles_h) * g.TH;
-        n0 = (m_tile / (g.tiles_w * g.tiles_h)) * g.TN;
-      }
+      int x0, y0, n0;
+      tile_origin(m_tile, x0, y0, n0);
       for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
         const uint32_t stage = it % Cfg::kStages;
         const uint32_t phase = (it / Cfg::kStages) & 1u;
@@ -186,95 +205,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
       tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
     }
+  } else if (warp == 3 && lane == 0) {
+    // ===================== TMA producer (residual chunks) =====================
+    if constexpr (kRes) {
+      uint32_t idx = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / num_n_tiles;
+        const int n_tile = tile % num_n_tiles;
+        int x0, y0, n0;
+        tile_origin(m_tile, x0, y0, n0);
+        for (int c = 0; c < NCHUNK; ++c, ++idx) {
+          const uint32_t slot = idx % Cfg::kResSlots;
+          const uint32_t phase = (idx / Cfg::kResSlots) & 1u;
+          mbar_wait(&res_empty[slot], phase ^ 1u);
+          mbar_expect_tx(&res_full[slot], g.chunk_bytes);
+          const int col = n_tile * BN + c * 32;  // boxes beyond N are zero-filled (keeps the slot sequence uniform)
+          if (g.conv)
+            tma_load_4d(sRes + slot * kChunk, &tmRes, &res_full[slot], col, x0, y0, n0);
+          else
+            tma_load_2d(sRes + slot * kChunk, &tmRes, &res_full[slot], col, m_tile * BM);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
     // warp w may only touch TMEM lanes [32*(w%4), +32): warps 4-7 and 8-11 each cover all 128 rows; the two groups
-    // split the tile's 32-column chunks between them. Per warp the chunk loop is software pipelined: the TMEM load
-    // and the residual loads of chunk i+1 are in flight while chunk i is converted and stored, and the first
-    // residual chunk is requested before the accumulator is even complete.
+    // split the tile's 32-column chunks between them.
     const int ew = warp & 3;
     const int hsel = (warp - 4) >> 2;
     const int r = ew * 32 + lane;
-    constexpr int NCHUNK = BN / 32;
+    const bool issuer = (ew == 0) && (lane == 0);
+    const int sw = (r >> 1) & 3;  // 64-byte swizzle: 16-byte piece index ^= address bits [7:8]
+    uint8_t* obuf_base = sOut + hsel * 2 * kChunk;
+    const int bar_id = 2 + hsel;
     constexpr int H0 = (NCHUNK + 1) / 2;
-    using T = typename C::T;
-    auto tile_row = [&](int tile_, long long& row_, bool& ok_) {
-      const int m_tile_ = tile_ / num_n_tiles;
-      if (!g.conv) {
-        row_ = static_cast<long long>(m_tile_) * BM + r;
-        ok_ = row_ < M;
-      } else {
-        const int x0 = (m_tile_ % g.tiles_w) * g.TW;
-        const int y0 = ((m_tile_ / g.tiles_w) % g.tiles_h) * g.TH;
-        const int n0 = (m_tile_ / (g.tiles_w * g.tiles_h)) * g.TN;
-        const int x = r % g.TW, y = (r / g.TW) % g.TH, n = r / (g.TW * g.TH);
-        ok_ = (n < g.TN) && (x0 + x < g.W) && (y0 + y < g.H) && (n0 + n < g.NI);
-        row_ = (static_cast<long long>(n0 + n) * g.H + (y0 + y)) * g.W + (x0 + x);
-      }
-    };
-    const int cbase_ = hsel ? H0 : 0;
-    const int ccount_ = hsel ? NCHUNK - H0 : H0;
-    // residual prefetch (kRes): this thread's row segment of tile `tile_` -> its slot in ring entry `slot`
-    auto prefetch_res = [&](int tile_, int slot) {
-      if constexpr (kRes) {
-        if (tile_ < num_tiles) {
-          long long row_;
-          bool ok_;
-          tile_row(tile_, row_, ok_);
-          if (ok_) {
-            const int n_tile_ = tile_ % num_n_tiles;
-            const T* src = static_cast<const T*>(ep.residual) + row_ * ep.ld_res + n_tile_ * BN;
-            const uint32_t dst = smem_u32(sres + (slot * BM + r) * Cfg::kResPitch);
-#pragma unroll
-            for (int i = 0; i < H0; ++i) {
-              if (i < ccount_) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const int cc = (cbase_ + i) * 32 + q * 8;
-                  if (n_tile_ * BN + cc < N)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + cc * 2), "l"(src + cc) : "memory");
-                }
-              }
-            }
-          }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-    };
-    if constexpr (kRes) {
-#pragma unroll
-      for (int dd = 0; dd < Cfg::kResDepth; ++dd) prefetch_res(blockIdx.x + dd * gridDim.x, dd);
-    }
-    uint32_t lt = 0;
+    uint32_t lt = 0, oc = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int m_tile = tile / num_n_tiles;
       const int n_tile = tile % num_n_tiles;
       const uint32_t acc = lt & 1u;
       const uint32_t acc_phase = (lt >> 1) & 1u;
-
-      long long row;
-      bool row_ok;
-      tile_row(tile, row, row_ok);
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+      int x0, y0, n0;
+      tile_origin(m_tile, x0, y0, n0);
 
       // ---- per-tile column constants -> smem: bias (+ the per-branch vector when the whole tile shares one group) ----
-      long long grp_first, grp_last;
+      long long grp_first, grp_last, row = 0;
+      bool row_ok = true;
       if (!g.conv) {
         const long long m0 = static_cast<long long>(m_tile) * BM;
         long long m1 = m0 + BM - 1;
         if (m1 > M - 1) m1 = M - 1;
         grp_first = m0 / ep.rows_per_group;
         grp_last = m1 / ep.rows_per_group;
+        row = m0 + r;
+        row_ok = row < M;
       } else {
-        const int x0 = (m_tile % g.tiles_w) * g.TW;
-        const int y0 = ((m_tile / g.tiles_w) % g.tiles_h) * g.TH;
-        const int n0 = (m_tile / (g.tiles_w * g.tiles_h)) * g.TN;
         int n1 = n0 + g.TN - 1;
         if (n1 > g.NI - 1) n1 = g.NI - 1;
         grp_first = (static_cast<long long>(n0) * g.H * g.W) / ep.rows_per_group;
         grp_last = (static_cast<long long>(n1 + 1) * g.H * g.W - 1) / ep.rows_per_group;
-        (void)x0;
-        (void)y0;
+        const int x = r % g.TW, y = (r / g.TW) % g.TH, n = r / (g.TW * g.TH);
+        row_ok = (n < g.TN) && (x0 + x < g.W) && (y0 + y < g.H) && (n0 + n < g.NI);
+        row = (static_cast<long long>(n0 + n) * g.H + (y0 + y)) * g.W + (x0 + x);
       }
       const bool rv_uniform = ep.rowvec != nullptr && grp_first == grp_last;
       float* sb = sbias + acc * 256;
@@ -294,81 +286,93 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const T* rv = (ep.rowvec && !rv_uniform && row_ok)
                         ? static_cast<const T*>(ep.rowvec) + (row / ep.rows_per_group) * ep.ld_rowvec
                         : nullptr;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
 
       if (ep.act != MIMO_ACT_GEGLU) {
         const int cbase = hsel ? H0 : 0;
         const int ccount = hsel ? NCHUNK - H0 : H0;
-        const bool res = kRes && row_ok;
-        T* outp = static_cast<T*>(ep.out) + row * ep.ldo;
-        constexpr int RD = Cfg::kResDepth > 0 ? Cfg::kResDepth : 1;
-        const uint8_t* rslot = sres + ((lt % RD) * BM + r) * Cfg::kResPitch;
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        if constexpr (kRes) {  // this tile's residual rows have landed (later tiles' copies may still be in flight)
-          if constexpr (Cfg::kResDepth == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
-          else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
 #pragma unroll
         for (int i = 0; i < H0; ++i) {
           if (i < ccount) {
             const int c = cbase + i;
+            uint8_t* obuf = obuf_base + (oc & 1u) * kChunk;
+            ++oc;
+            if (issuer) tma_store_wait_read0();  // see "Staging-buffer reuse" below
             uint32_t v[32];
             tmem_ld_x32(taddr + c * 32, v);
+            const uint8_t* rrow = nullptr;
+            uint32_t rslot = 0;
+            if constexpr (kRes) {
+              const uint32_t idx = lt * NCHUNK + c;
+              rslot = idx % Cfg::kResSlots;
+              mbar_wait(&res_full[rslot], (idx / Cfg::kResSlots) & 1u);
+              rrow = sRes + rslot * kChunk + r * 64;
+            }
             tmem_ld_wait();
             const int col0 = n_tile * BN + c * 32;
-            if (row_ok) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int col = col0 + q * 8;
-                if (col < N) {  // N % 8 == 0
-                  float f[8];
-                  const float4 b0 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8);
-                  const float4 b1 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8 + 4);
-                  f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x;
-                  f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
-                  f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z;
-                  f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
-                  f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x;
-                  f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
-                  f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z;
-                  f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
-                  if (rv) {
-                    const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + col));
-                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+            for (int q = 0; q < 4; ++q) {
+              float f[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8 + 4);
+              f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x;
+              f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
+              f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z;
+              f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
+              f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x;
+              f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
+              f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z;
+              f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
+              if (rv && col0 + q * 8 < N) {
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + col0 + q * 8));
+                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const float2 t = C::unpack(bw[j]);
-                      f[2 * j] += t.x;
-                      f[2 * j + 1] += t.y;
-                    }
-                  }
-                  if (res) {
-                    const uint4 rr = *reinterpret_cast<const uint4*>(rslot + (c * 32 + q * 8) * 2);
-                    const uint32_t bw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const float2 t = C::unpack(bw[j]);
-                      f[2 * j] += t.x;
-                      f[2 * j + 1] += t.y;
-                    }
-                  }
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    f[j] *= ep.scale;
-                    if (ep.act == MIMO_ACT_SILU) f[j] = silu_f(f[j]);
-                  }
-                  uint4 o;
-                  o.x = C::pack(f[0], f[1]);
-                  o.y = C::pack(f[2], f[3]);
-                  o.z = C::pack(f[4], f[5]);
-                  o.w = C::pack(f[6], f[7]);
-                  *reinterpret_cast<uint4*>(outp + col) = o;
+                for (int j = 0; j < 4; ++j) {
+                  const float2 t = C::unpack(bw[j]);
+                  f[2 * j] += t.x;
+                  f[2 * j + 1] += t.y;
                 }
               }
+              if constexpr (kRes) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(rrow + ((q ^ sw) << 4));
+                const uint32_t bw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 t = C::unpack(bw[j]);
+                  f[2 * j] += t.x;
+                  f[2 * j + 1] += t.y;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[j] *= ep.scale;
+                if (ep.act == MIMO_ACT_SILU) f[j] = silu_f(f[j]);
+              }
+              uint4 o;
+              o.x = C::pack(f[0], f[1]);
+              o.y = C::pack(f[2], f[3]);
+              o.z = C::pack(f[4], f[5]);
+              o.w = C::pack(f[6], f[7]);
+              *reinterpret_cast<uint4*>(obuf + r * 64 + ((q ^ sw) << 4)) = o;
+            }
+            if constexpr (kRes) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&res_empty[rslot]);
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (issuer) {
+              if (g.conv)
+                tma_store_4d(&tmOut, obuf, col0, x0, y0, n0);
+              else
+                tma_store_2d(&tmOut, obuf, col0, m_tile * BM);
+              tma_store_commit();
             }
           }
         }
-        if constexpr (kRes) prefetch_res(tile + Cfg::kResDepth * static_cast<int>(gridDim.x), lt % RD);
       } else {
         // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates; 32-column pairs are split
         // between the two warp groups.
@@ -377,34 +381,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         constexpr int P0 = (NPAIR + 1) / 2;
         const int pbase = hsel ? P0 : 0;
         const int pcount = hsel ? NPAIR - P0 : P0;
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
 #pragma unroll
         for (int i = 0; i < P0; ++i) {
           if (i < pcount) {
             const int c = pbase + i;
+            uint8_t* obuf = obuf_base + (oc & 1u) * kChunk;
+            ++oc;
+            if (issuer) tma_store_wait_read0();
             uint32_t v[32], gt[32];
             tmem_ld_x32(taddr + c * 32, v);
             tmem_ld_x32(taddr + HALF + c * 32, gt);
             tmem_ld_wait();
-            const int ocol0 = n_tile * HALF + c * 32;  // output column
-            if (row_ok) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float f[8];
+            for (int q = 0; q < 4; ++q) {
+              float f[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float fv = __uint_as_float(v[q * 8 + j]) + sb[c * 32 + q * 8 + j];
-                  const float fg = __uint_as_float(gt[q * 8 + j]) + sb[HALF + c * 32 + q * 8 + j];
-                  f[j] = fv * gelu_erf_fast(fg);
-                }
-                uint4 o;
-                o.x = C::pack(f[0], f[1]);
-                o.y = C::pack(f[2], f[3]);
-                o.z = C::pack(f[4], f[5]);
-                o.w = C::pack(f[6], f[7]);
-                *reinterpret_cast<uint4*>(static_cast<T*>(ep.out) + row * ep.ldo + ocol0 + q * 8) = o;
+              for (int j = 0; j < 8; ++j) {
+                const float fv = __uint_as_float(v[q * 8 + j]) + sb[c * 32 + q * 8 + j];
+                const float fg = __uint_as_float(gt[q * 8 + j]) + sb[HALF + c * 32 + q * 8 + j];
+                f[j] = fv * gelu_erf_fast(fg);
               }
+              uint4 o;
+              o.x = C::pack(f[0], f[1]);
+              o.y = C::pack(f[2], f[3]);
+              o.z = C::pack(f[4], f[5]);
+              o.w = C::pack(f[6], f[7]);
+              *reinterpret_cast<uint4*>(obuf + r * 64 + ((q ^ sw) << 4)) = o;
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (issuer) {
+              tma_store_2d(&tmOut, obuf, n_tile * HALF + c * 32, m_tile * BM);
+              tma_store_commit();
             }
           }
         }
@@ -414,7 +422,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    if constexpr (kRes) asm volatile("cp.async.wait_all;" ::: "memory");
+    if (issuer) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -425,12 +433,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   }
 }
 
+// Staging-buffer reuse: a group's two 8 KiB buffers alternate per chunk. The issuer executes
+// cp.async.bulk.wait_group.read 0 at the START of chunk i, i.e. after it committed store(i-1) and before it joins
+// barrier(i); every thread writes buffer (i+1)&1 only after barrier(i), by which time stores <= i-1 — including
+// store(i-1), the last reader of that buffer — have finished reading shared memory.
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+struct Maps {
+  CUtensorMap a0, a1, b, out, res;
+};
+
 template <int BN, bool kBf16, bool kRes>
-static int launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, int M, int N, int mt,
-                      int nt, int nkb, const ConvGeom& g, const EpiArgs& ep, cudaStream_t st) {
+static int launch_cfg(const Maps& m, int M, int N, int mt, int nt, int nkb, const ConvGeom& g, const EpiArgs& ep,
+                      cudaStream_t st) {
   using Cfg = GemmCfg<BN, kRes>;
   auto kern = gemm_tcgen05_kernel<BN, kBf16, kRes>;
   static bool attr_done = false;  // per instantiation
@@ -441,29 +458,28 @@ static int launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
   }
   const int tiles = mt * nt;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a0, a1, b, M, N, mt, nt, nkb, g, ep);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(m.a0, m.a1, m.b, m.out, m.res, M, N, mt, nt, nkb, g, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("gemm launch", e);
   return MIMO_OK;
 }
 
 template <bool kBf16>
-static int launch_bn(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, int M, int N,
-                     int mt, int nt, int nkb, const ConvGeom& g, const EpiArgs& ep, cudaStream_t st) {
-  const bool res = ep.residual != nullptr && ep.act != MIMO_ACT_GEGLU;
+static int launch_bn(int bn, bool res, const Maps& m, int M, int N, int mt, int nt, int nkb, const ConvGeom& g,
+                     const EpiArgs& ep, cudaStream_t st) {
   switch (bn) {
     case 64:
-      return res ? launch_cfg<64, kBf16, true>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st)
-                 : launch_cfg<64, kBf16, false>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+      return res ? launch_cfg<64, kBf16, true>(m, M, N, mt, nt, nkb, g, ep, st)
+                 : launch_cfg<64, kBf16, false>(m, M, N, mt, nt, nkb, g, ep, st);
     case 128:
-      return res ? launch_cfg<128, kBf16, true>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st)
-                 : launch_cfg<128, kBf16, false>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+      return res ? launch_cfg<128, kBf16, true>(m, M, N, mt, nt, nkb, g, ep, st)
+                 : launch_cfg<128, kBf16, false>(m, M, N, mt, nt, nkb, g, ep, st);
     case 160:
-      return res ? launch_cfg<160, kBf16, true>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st)
-                 : launch_cfg<160, kBf16, false>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+      return res ? launch_cfg<160, kBf16, true>(m, M, N, mt, nt, nkb, g, ep, st)
+                 : launch_cfg<160, kBf16, false>(m, M, N, mt, nt, nkb, g, ep, st);
     case 256:
-      return res ? launch_cfg<256, kBf16, true>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st)
-                 : launch_cfg<256, kBf16, false>(a0, a1, b, M, N, mt, nt, nkb, g, ep, st);
+      return res ? launch_cfg<256, kBf16, true>(m, M, N, mt, nt, nkb, g, ep, st)
+                 : launch_cfg<256, kBf16, false>(m, M, N, mt, nt, nkb, g, ep, st);
   }
   return set_error(MIMO_ERR_ARG, "gemm: unsupported BN");
 }
@@ -496,19 +512,14 @@ int pick_bn(int N, bool geglu, long long m_tiles) {
   return best;
 }
 
-static EpiArgs make_epi(const mimo_epilogue& e, void* out, long long ldo, int N) {
+static EpiArgs make_epi(const mimo_epilogue& e, int N) {
   EpiArgs a;
   a.bias = e.bias;
   a.rowvec = e.rowvec;
-  a.residual = e.residual;
-  a.out = out;
   a.rows_per_group = e.rows_per_group > 0 ? e.rows_per_group : 1;
-  a.ld_rowvec = e.ld_rowvec;
-  a.ld_res = e.ld_res;
-  a.ldo = ldo;
+  a.ld_rowvec = e.ld_rowvec > 0 ? e.ld_rowvec : N;
   a.scale = e.scale;
   a.act = e.act;
-  if (a.ld_rowvec <= 0) a.ld_rowvec = N;
   return a;
 }
 
@@ -540,31 +551,44 @@ extern "C" int mimo_gemm(const mimo_gemm_params* p, void* stream) {
   const int kb0 = (p->K + BK - 1) / BK;
   const int kb1 = (K1 + BK - 1) / BK;
   const int nkb = kb0 + kb1;
+  const bool res = p->ep.residual != nullptr && !geglu;
 
-  CUtensorMap ta, ta1, tb;
+  Maps m;
   const uint64_t adim[2] = {static_cast<uint64_t>(p->K), static_cast<uint64_t>(p->M)};
   const uint64_t astr[1] = {static_cast<uint64_t>(p->lda) * 2};
   const uint32_t abox[2] = {BK, BM};
-  if (int rc = encode_tmap(&ta, p->dtype, 2, p->a, adim, astr, abox)) return rc;
-  ta1 = ta;
+  if (int rc = encode_tmap(&m.a0, p->dtype, 2, p->a, adim, astr, abox)) return rc;
+  m.a1 = m.a0;
   if (K1) {
     const uint64_t a1dim[2] = {static_cast<uint64_t>(K1), static_cast<uint64_t>(p->M)};
     const uint64_t a1str[1] = {static_cast<uint64_t>(p->lda1) * 2};
-    if (int rc = encode_tmap(&ta1, p->dtype, 2, p->a1, a1dim, a1str, abox)) return rc;
+    if (int rc = encode_tmap(&m.a1, p->dtype, 2, p->a1, a1dim, a1str, abox)) return rc;
   }
   const uint64_t bdim[2] = {static_cast<uint64_t>(p->K + K1), static_cast<uint64_t>(p->N)};
   const uint64_t bstr[1] = {static_cast<uint64_t>(p->ldw) * 2};
   const uint32_t bbox[2] = {BK, static_cast<uint32_t>(bn)};
-  if (int rc = encode_tmap(&tb, p->dtype, 2, p->w, bdim, bstr, bbox)) return rc;
+  if (int rc = encode_tmap(&m.b, p->dtype, 2, p->w, bdim, bstr, bbox)) return rc;
+  // output / residual: 128-row x 32-column boxes, 64-byte swizzle
+  const int n_out = geglu ? p->N / 2 : p->N;
+  const uint64_t odim[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(p->M)};
+  const uint64_t ostr[1] = {static_cast<uint64_t>(p->ldo) * 2};
+  const uint32_t obox[2] = {32, BM};
+  if (int rc = encode_tmap(&m.out, p->dtype, 2, p->out, odim, ostr, obox, 64)) return rc;
+  m.res = m.out;
+  if (res) {
+    const uint64_t rstr[1] = {static_cast<uint64_t>(p->ep.ld_res) * 2};
+    if (int rc = encode_tmap(&m.res, p->dtype, 2, p->ep.residual, odim, rstr, obox, 64)) return rc;
+  }
 
   ConvGeom g = {};
   g.kb0 = kb0;
   g.kb1 = kb1;
   g.c0 = p->K;
-  EpiArgs ep = make_epi(p->ep, p->out, p->ldo, p->N);
+  g.chunk_bytes = kChunk;
+  EpiArgs ep = make_epi(p->ep, p->N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == MIMO_BF16) return launch_bn<true>(bn, ta, ta1, tb, p->M, p->N, mt, nt, nkb, g, ep, st);
-  return launch_bn<false>(bn, ta, ta1, tb, p->M, p->N, mt, nt, nkb, g, ep, st);
+  if (p->dtype == MIMO_BF16) return launch_bn<true>(bn, res, m, p->M, p->N, mt, nt, nkb, g, ep, st);
+  return launch_bn<false>(bn, res, m, p->M, p->N, mt, nt, nkb, g, ep, st);
 }
 
 extern "C" int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream) {
@@ -575,6 +599,7 @@ extern "C" int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream) {
   if ((p->c0 % 8) || (c1 % 8) || (p->cout % 8) || (p->ldo % 8))
     return set_error(MIMO_ERR_ARG, "mimo_conv3x3: channel counts must be multiples of 8");
   if (p->ep.act == MIMO_ACT_GEGLU) return set_error(MIMO_ERR_ARG, "mimo_conv3x3: GEGLU not supported");
+  if (p->ep.residual && (p->ep.ld_res % 8)) return set_error(MIMO_ERR_ARG, "mimo_conv3x3: ld_res % 8 != 0");
   if (int rc = ensure_device()) return rc;
 
   ConvGeom g = {};
@@ -598,43 +623,43 @@ extern "C" int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream) {
   g.kb0 = (p->c0 + BK - 1) / BK;
   g.kb1 = (c1 + BK - 1) / BK;
   g.a_bytes = g.TW * g.TH * g.TN * BK * 2;
+  g.chunk_bytes = g.TW * g.TH * g.TN * 64;
   const int mt = g.tiles_w * g.tiles_h * tiles_n;
   const int bn = pick_bn(p->cout, false, mt);
   const int nt = (p->cout + bn - 1) / bn;
   const int nkb = 9 * (g.kb0 + g.kb1);
   const long long Mrows = static_cast<long long>(p->n) * p->h * p->w_;
   if (Mrows > 0x7fffffffLL) return set_error(MIMO_ERR_ARG, "mimo_conv3x3: too many pixels");
+  const bool res = p->ep.residual != nullptr;
 
-  CUtensorMap ta0, ta1, tb;
-  {
-    const uint64_t dim[4] = {static_cast<uint64_t>(p->c0), static_cast<uint64_t>(p->w_),
-                             static_cast<uint64_t>(p->h), static_cast<uint64_t>(p->n)};
-    const uint64_t str[3] = {static_cast<uint64_t>(p->c0) * 2, static_cast<uint64_t>(p->w_) * p->c0 * 2,
-                             static_cast<uint64_t>(p->h) * p->w_ * p->c0 * 2};
-    const uint32_t box[4] = {BK, static_cast<uint32_t>(g.TW), static_cast<uint32_t>(g.TH),
+  Maps m;
+  auto nhwc_map = [&](CUtensorMap* tm, const void* base, int c, long long pitch, uint32_t box_c, int swz) {
+    const uint64_t dim[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(p->w_), static_cast<uint64_t>(p->h),
+                             static_cast<uint64_t>(p->n)};
+    const uint64_t str[3] = {static_cast<uint64_t>(pitch) * 2, static_cast<uint64_t>(p->w_) * pitch * 2,
+                             static_cast<uint64_t>(p->h) * p->w_ * pitch * 2};
+    const uint32_t box[4] = {box_c, static_cast<uint32_t>(g.TW), static_cast<uint32_t>(g.TH),
                              static_cast<uint32_t>(g.TN)};
-    if (int rc = encode_tmap(&ta0, p->dtype, 4, p->x0, dim, str, box)) return rc;
-  }
-  if (c1) {
-    const uint64_t dim[4] = {static_cast<uint64_t>(c1), static_cast<uint64_t>(p->w_),
-                             static_cast<uint64_t>(p->h), static_cast<uint64_t>(p->n)};
-    const uint64_t str[3] = {static_cast<uint64_t>(c1) * 2, static_cast<uint64_t>(p->w_) * c1 * 2,
-                             static_cast<uint64_t>(p->h) * p->w_ * c1 * 2};
-    const uint32_t box[4] = {BK, static_cast<uint32_t>(g.TW), static_cast<uint32_t>(g.TH),
-                             static_cast<uint32_t>(g.TN)};
-    if (int rc = encode_tmap(&ta1, p->dtype, 4, p->x1, dim, str, box)) return rc;
-  } else {
-    ta1 = ta0;
-  }
+    return encode_tmap(tm, p->dtype, 4, base, dim, str, box, swz);
+  };
+  if (int rc = nhwc_map(&m.a0, p->x0, p->c0, p->c0, BK, 128)) return rc;
+  m.a1 = m.a0;
+  if (c1)
+    if (int rc = nhwc_map(&m.a1, p->x1, c1, c1, BK, 128)) return rc;
   {
     const uint64_t dim[2] = {static_cast<uint64_t>(9) * g.ctot, static_cast<uint64_t>(p->cout)};
     const uint64_t str[1] = {static_cast<uint64_t>(9) * g.ctot * 2};
     const uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
-    if (int rc = encode_tmap(&tb, p->dtype, 2, p->w, dim, str, box)) return rc;
+    if (int rc = encode_tmap(&m.b, p->dtype, 2, p->w, dim, str, box)) return rc;
   }
-  EpiArgs ep = make_epi(p->ep, p->out, p->ldo, p->cout);
+  if (int rc = nhwc_map(&m.out, p->out, p->cout, p->ldo, 32, 64)) return rc;
+  m.res = m.out;
+  if (res)
+    if (int rc = nhwc_map(&m.res, p->ep.residual, p->cout, p->ep.ld_res, 32, 64)) return rc;
+
+  EpiArgs ep = make_epi(p->ep, p->cout);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dtype == MIMO_BF16)
-    return launch_bn<true>(bn, ta0, ta1, tb, static_cast<int>(Mrows), p->cout, mt, nt, nkb, g, ep, st);
-  return launch_bn<false>(bn, ta0, ta1, tb, static_cast<int>(Mrows), p->cout, mt, nt, nkb, g, ep, st);
+    return launch_bn<true>(bn, res, m, static_cast<int>(Mrows), p->cout, mt, nt, nkb, g, ep, st);
+  return launch_bn<false>(bn, res, m, static_cast<int>(Mrows), p->cout, mt, nt, nkb, g, ep, st);
 }

@@ -16,7 +16,7 @@ int num_sms();
 // rank-`rank` tiled tensor map, 16-bit elements, 128-byte swizzle, zero OOB fill.
 // dims[0] is the contiguous dimension; strides_bytes[i] is the byte stride of dims[i+1].
 int encode_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box);
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 inline unsigned div_up(long long a, long long b) { return static_cast<unsigned>((a + b - 1) / b); }
 
