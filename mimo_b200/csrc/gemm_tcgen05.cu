@@ -208,22 +208,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == 3 && lane == 0) {
     // ===================== TMA producer (residual chunks) =====================
     if constexpr (kRes) {
-      uint32_t idx = 0;
+      // Each epilogue column group owns half of the slots as a private ring (a barrier shared by consumers that can
+      // sit in different phases would let the later one alias a completed phase of the same parity).
+      constexpr int SH = Cfg::kResSlots / 2;
+      constexpr int H0 = (NCHUNK + 1) / 2;
+      uint32_t cnt[2] = {0, 0};
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / num_n_tiles;
         const int n_tile = tile % num_n_tiles;
         int x0, y0, n0;
         tile_origin(m_tile, x0, y0, n0);
-        for (int c = 0; c < NCHUNK; ++c, ++idx) {
-          const uint32_t slot = idx % Cfg::kResSlots;
-          const uint32_t phase = (idx / Cfg::kResSlots) & 1u;
-          mbar_wait(&res_empty[slot], phase ^ 1u);
-          mbar_expect_tx(&res_full[slot], g.chunk_bytes);
-          const int col = n_tile * BN + c * 32;  // boxes beyond N are zero-filled (keeps the slot sequence uniform)
-          if (g.conv)
-            tma_load_4d(sRes + slot * kChunk, &tmRes, &res_full[slot], col, x0, y0, n0);
-          else
-            tma_load_2d(sRes + slot * kChunk, &tmRes, &res_full[slot], col, m_tile * BM);
+        for (int i = 0; i < H0; ++i) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (i >= (h ? NCHUNK - H0 : H0)) continue;
+            const int c = (h ? H0 : 0) + i;
+            const uint32_t k = cnt[h]++;
+            const uint32_t slot = h * SH + k % SH;
+            mbar_wait(&res_empty[slot], ((k / SH) & 1u) ^ 1u);
+            mbar_expect_tx(&res_full[slot], g.chunk_bytes);
+            const int col = n_tile * BN + c * 32;  // boxes beyond N are zero-filled (keeps the slot sequence uniform)
+            if (g.conv)
+              tma_load_4d(sRes + slot * kChunk, &tmRes, &res_full[slot], col, x0, y0, n0);
+            else
+              tma_load_2d(sRes + slot * kChunk, &tmRes, &res_full[slot], col, m_tile * BM);
+          }
         }
       }
     }
@@ -239,7 +248,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     uint8_t* obuf_base = sOut + hsel * 2 * kChunk;
     const int bar_id = 2 + hsel;
     constexpr int H0 = (NCHUNK + 1) / 2;
-    uint32_t lt = 0, oc = 0;
+    uint32_t lt = 0, oc = 0, rc = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int m_tile = tile / num_n_tiles;
       const int n_tile = tile % num_n_tiles;
@@ -306,9 +315,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const uint8_t* rrow = nullptr;
             uint32_t rslot = 0;
             if constexpr (kRes) {
-              const uint32_t idx = lt * NCHUNK + c;
-              rslot = idx % Cfg::kResSlots;
-              mbar_wait(&res_full[rslot], (idx / Cfg::kResSlots) & 1u);
+              constexpr int SH = Cfg::kResSlots / 2;
+              const uint32_t k = rc++;
+              rslot = hsel * SH + k % SH;
+              mbar_wait(&res_full[rslot], (k / SH) & 1u);
               rrow = sRes + rslot * kChunk + r * 64;
             }
             tmem_ld_wait();
@@ -541,6 +551,8 @@ extern "C" int mimo_gemm(const mimo_gemm_params* p, void* stream) {
     return set_error(MIMO_ERR_ARG, "mimo_gemm: K, N, lda, ldw, ldo must be multiples of 8");
   if (p->ep.residual && (p->ep.ld_res % 8)) return set_error(MIMO_ERR_ARG, "mimo_gemm: ld_res % 8 != 0");
   const bool geglu = p->ep.act == MIMO_ACT_GEGLU;
+  if (geglu && (p->ep.residual || p->ep.rowvec))
+    return set_error(MIMO_ERR_ARG, "mimo_gemm: GEGLU takes neither a residual nor a row vector");
   if (int rc = ensure_device()) return rc;
   const int mt = (p->M + BM - 1) / BM;
   const int bn = pick_bn(p->N, geglu, mt);
