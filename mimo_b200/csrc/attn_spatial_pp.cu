@@ -7,6 +7,9 @@
 //   warp 2        : TMEM allocator (512 columns: S_A, S_B, O_A, O_B)
 //   warps 4-7     : softmax warpgroup A (one thread per query row = TMEM lane)
 //   warps 8-11    : softmax warpgroup B
+// A softmax thread pulls its whole 128-key row of S into registers (128 of the 168 the launch bound allows) and
+// releases S_X at once, so Q_X K[j+1]^T runs underneath the exponentials of tile j and
+// the MUFU pipe - the bound of this kernel at d = 40 - never waits for the tensor pipe.
 // Softmax: base-2 exponentials (ex2.approx), fp32 running sum, LAZY rescaling — the reference maximum of a row is only
 // moved (and O rescaled in TMEM) when the tile maximum exceeds it by more than 2^8, which keeps P within fp16
 // range and is exact after the final division by the row sum. P goes to shared memory as the 128B-swizzled K-major A
@@ -63,7 +66,8 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t* s_full = bars + 9;      // 2 (per query tile)
   uint64_t* p_full = bars + 11;     // 2
   uint64_t* o_done = bars + 13;     // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* s_free = bars + 15;     // 2: the softmax group holds S_X in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,6 +98,7 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 128);
       mbar_init(&o_done[s], 1);
+      mbar_init(&s_free[s], 4);
     }
     fence_mbar_init();
   }
@@ -104,7 +109,8 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   // columns: S_A [0,128)  S_B [128,256)  O_A [256,384)  O_B [384,512)
 
-  if (warp == 0 && lane == 0) {
+  if (warp < 4) {
+   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     mbar_expect_tx(q_full, Cfg::kQBytes);
 #pragma unroll
@@ -155,6 +161,15 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int j = 0; j < T; ++j) {
       const int stage = j % ST;
       const uint32_t v_addr = smem_u32(sV + stage * Cfg::kTile);
+      // S_X(j+1) as soon as group X has S_X(j) in registers
+      if (j + 1 < T) {
+        mbar_wait(&k_full[(j + 1) % ST], ((j + 1) / ST) & 1u);
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(&s_free[x], j & 1);
+          tc_fence_after();
+          issue_qk(x, j + 1);
+        }
+      }
       for (int x = 0; x < 2; ++x) {
         mbar_wait(&p_full[x], j & 1);
         if (x == 0) mbar_wait(&v_full[stage], (j / ST) & 1u);
@@ -168,16 +183,10 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
         if (x == 1) tc_commit(&v_empty[stage]);  // both query tiles are done with V[j]
         tc_commit(&o_done[x]);
-        if (j + 1 < T) {
-          if (x == 0) {
-            mbar_wait(&k_full[(j + 1) % ST], ((j + 1) / ST) & 1u);
-            tc_fence_after();
-          }
-          issue_qk(x, j + 1);
-        }
       }
     }
-  } else if (warp >= 4) {
+   }
+  } else {
     // ===================== softmax warpgroups =====================
     const int x = (warp - 4) >> 2;  // query tile A / B
     const int ew = warp & 3;
@@ -197,28 +206,31 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (valid > BKV) valid = BKV;
       mbar_wait(&s_full[x], j & 1);
       tc_fence_after();
-      // ---- pass 1: tile maximum (4 independent chains) ----
+      // ---- the whole row of S -> registers, then hand S_X back to the tensor pipe ----
+      uint32_t sv[4][32];
+      tmem_ld_x32(tS, sv[0]);
+      tmem_ld_x32(tS + 32, sv[1]);
+      tmem_ld_x32(tS + 64, sv[2]);
+      tmem_ld_x32(tS + 96, sv[3]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[x]);
+      // ---- tile maximum (4 independent chains) ----
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (valid == BKV) {
 #pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        uint32_t v0[32], v1[32];
-        tmem_ld_x32(tS + hlf * 64, v0);
-        tmem_ld_x32(tS + hlf * 64 + 32, v1);
-        tmem_ld_wait();
-        if (valid == BKV) {
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+          mx2 = fmaxf(mx2, __uint_as_float(sv[2][i]));
+          mx3 = fmaxf(mx3, __uint_as_float(sv[3][i]));
+        }
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
-            mx1 = fmaxf(mx1, __uint_as_float(v0[i + 1]));
-            mx2 = fmaxf(mx2, __uint_as_float(v1[i]));
-            mx3 = fmaxf(mx3, __uint_as_float(v1[i + 1]));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (hlf * 64 + i < valid) mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
-            if (hlf * 64 + 32 + i < valid) mx1 = fmaxf(mx1, __uint_as_float(v1[i]));
-          }
+        for (int i = 0; i < 128; ++i) {
+          if (i >= valid) sv[i >> 5][i & 31] = __float_as_uint(-INFINITY);  // exp2 -> 0: padded keys leave P and l
+          mx0 = fmaxf(mx0, __uint_as_float(sv[i >> 5][i & 31]));
         }
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
@@ -236,45 +248,29 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           l *= alpha;
         }
       }
-      // P_X (and O_X) may only be overwritten once the previous P_X.V has retired
-      if (j > 0) {
-        mbar_wait(&o_done[x], (j - 1) & 1);
-        tc_fence_after();
-      }
-      // ---- pass 2: probabilities -> swizzled smem ----
+      // ---- probabilities -> swizzled smem ----
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       const float nm = -m_ref;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(tS + c * 32, v);
-        tmem_ld_wait();
         uint32_t pk[16];
-        if (valid == BKV) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sc, nm));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sc, nm));
-            const float p2 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 2]), sc, nm));
-            const float p3 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 3]), sc, nm));
-            s0 += p0;
-            s1 += p1;
-            s2 += p2;
-            s3 += p3;
-            pk[i] = C::pack(p0, p1);
-            pk[i + 1] = C::pack(p2, p3);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c0 = c * 32 + 2 * i;
-            float p0 = 0.f, p1 = 0.f;
-            if (c0 < valid) p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sc, nm));
-            if (c0 + 1 < valid) p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sc, nm));
-            s0 += p0;
-            s1 += p1;
-            pk[i] = C::pack(p0, p1);
-          }
+        for (int i = 0; i < 16; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i]), sc, nm));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i + 1]), sc, nm));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i + 2]), sc, nm));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i + 3]), sc, nm));
+          s0 += p0;
+          s1 += p1;
+          s2 += p2;
+          s3 += p3;
+          pk[i] = C::pack(p0, p1);
+          pk[i + 1] = C::pack(p2, p3);
+        }
+        // P_X (and O_X) may only be overwritten once the previous P_X.V has retired
+        if (c == 0 && j > 0) {
+          mbar_wait(&o_done[x], (j - 1) & 1);
+          tc_fence_after();
         }
         uint8_t* line = prow + (c >> 1) * kChunkBytes;
 #pragma unroll
