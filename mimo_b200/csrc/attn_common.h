@@ -17,6 +17,8 @@ struct AttnArgs {
   const int* bank_index;
   void* out;
   long long ld_out;
+  int variant;        // debug (mimo_debug_attn_variant) bits: 4 = P stores deferred, 8 = no stagger
+  long long* trace;   // debug (mimo_debug_attn_trace): clock64 timeline of CTA (0,0,0), or nullptr
 };
 
 // two Q tiles per CTA (grid.x = ceil(lq / 256)); dp <= 128

@@ -304,6 +304,11 @@ extern "C" int mimo_debug_attn_variant(int v) {
   g_attn_variant = v;
   return 0;
 }
+static long long* g_attn_trace = nullptr;
+extern "C" int mimo_debug_attn_trace(void* buf) {  // >= 5120 int64 of device memory, or NULL
+  g_attn_trace = static_cast<long long*>(buf);
+  return 0;
+}
 
 extern "C" int mimo_attn_spatial(const mimo_attn_params* p, void* stream) {
   if (!p || !p->q || !p->k || !p->v || !p->out) return set_error(MIMO_ERR_ARG, "mimo_attn_spatial: null pointer");
@@ -316,6 +321,8 @@ extern "C" int mimo_attn_spatial(const mimo_attn_params* p, void* stream) {
 
   AttnArgs a;
   a.lq = p->lq;
+  a.variant = g_attn_variant;
+  a.trace = g_attn_trace;
   a.lb = has_bank ? p->lb : 0;
   a.heads = p->heads;
   a.d = p->d;

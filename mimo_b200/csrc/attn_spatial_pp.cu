@@ -67,14 +67,15 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t* p_full = bars + 11;     // 2
   uint64_t* o_done = bars + 13;     // 2
   uint64_t* s_free = bars + 15;     // 2: the softmax group holds S_X in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* stagger = bars + 17;    // 1: tile A finished its first exponentials -> tile B may start (anti-phase)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int q_pair = blockIdx.x;
   const int h = blockIdx.y;
   const int n = blockIdx.z;
-  const int bidx = a.bank_index ? a.bank_index[n] : -1;
+  const int bidx = __shfl_sync(0xffffffffu, a.bank_index ? a.bank_index[n] : -1, 0);
   const int T = a.n_self_tiles + (bidx >= 0 ? a.n_bank_tiles : 0);
 
   if (warp == 0 && lane == 0) {
@@ -90,23 +91,24 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     mbar_init(q_full, 1);
     for (int s = 0; s < ST; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
+      mbar_init(&k_empty[s], 2);  // one tcgen05.commit per query tile
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_empty[s], 2);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
+      mbar_init(&p_full[s], 4);
       mbar_init(&o_done[s], 1);
       mbar_init(&s_free[s], 4);
     }
+    mbar_init(stagger, 4);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   // columns: S_A [0,128)  S_B [128,256)  O_A [256,384)  O_B [384,512)
 
   if (warp < 4) {
@@ -135,55 +137,68 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int ch = 0; ch < NCH; ++ch)
         tma_load_4d(sV + stage * Cfg::kTile + ch * kChunkBytes, bank ? &tmBV : &tmV, &v_full[stage], ch * 64, h, row0, img);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+   } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers: warp 1 drives query tile A, warp 3 tile B =====================
+    // The whole warp runs the (uniform) control flow and one elected lane issues the tcgen05 instructions, so the
+    // descriptors stay in uniform registers: a lane-0-only branch costs ~150 clk of scalar code per MMA here, more
+    // than the MMA itself, and made the issuer the bottleneck of the kernel.
+    const int x = warp == 3 ? 1 : 0;
     const uint32_t idesc_qk = make_idesc_f16(BQ, BKV, kBf16, false, false);
     const uint32_t idesc_pv = make_idesc_f16(BQ, a.dp, kBf16, false, true);  // B (= V) is MN-major
     const int ksteps_qk = a.dp / 16;
-    const uint32_t q_addr = smem_u32(sQ);
-    const uint32_t p_addr = smem_u32(sP);
-    auto issue_qk = [&](int x, int j) {
+    const uint32_t qa = smem_u32(sQ) + x * Cfg::kTile;
+    const uint32_t pa0 = smem_u32(sP) + x * 2 * kChunkBytes;
+    const uint32_t tS = tmem_base + x * 128;
+    const uint32_t tO = tmem_base + 256 + x * 128;
+    long long* tr = (a.trace && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+                        ? a.trace + 4096 + x * 512
+                        : nullptr;
+    auto issue_qk = [&](int j) {
       const uint32_t k_addr = smem_u32(sK + (j % ST) * Cfg::kTile);
-      const uint32_t qa = q_addr + x * Cfg::kTile;
-      for (int ks = 0; ks < ksteps_qk; ++ks) {
-        const uint32_t off = (ks >> 2) * kChunkBytes + (ks & 3) * 32;
-        umma_ss(tmem_base + x * 128, make_smem_desc_sw128(qa + off, 16, 1024),
-                make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0 ? 1u : 0u);
+      if (elect_one()) {
+        for (int ks = 0; ks < ksteps_qk; ++ks) {
+          const uint32_t off = (ks >> 2) * kChunkBytes + (ks & 3) * 32;
+          umma_ss(tS, make_smem_desc_sw128(qa + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024),
+                  idesc_qk, ks != 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[x]);
+        tc_commit(&k_empty[j % ST]);  // released once both query tiles have consumed K[j]
       }
-      tc_commit(&s_full[x]);
-      if (x == 1) tc_commit(&k_empty[j % ST]);  // both query tiles have consumed K[j]
+      __syncwarp();
     };
     mbar_wait(q_full, 0);
     mbar_wait(&k_full[0], 0);
     tc_fence_after();
-    issue_qk(0, 0);
-    issue_qk(1, 0);
+    issue_qk(0);
     for (int j = 0; j < T; ++j) {
       const int stage = j % ST;
-      const uint32_t v_addr = smem_u32(sV + stage * Cfg::kTile);
-      // S_X(j+1) as soon as group X has S_X(j) in registers
-      if (j + 1 < T) {
+      if (j + 1 < T) {  // S_X(j+1) as soon as the softmax group has S_X(j) in registers
+        mbar_wait(&s_free[x], j & 1);
+        if (tr && j < 64) tr[8 * j] = clock64();
         mbar_wait(&k_full[(j + 1) % ST], ((j + 1) / ST) & 1u);
-        for (int x = 0; x < 2; ++x) {
-          mbar_wait(&s_free[x], j & 1);
-          tc_fence_after();
-          issue_qk(x, j + 1);
-        }
-      }
-      for (int x = 0; x < 2; ++x) {
-        mbar_wait(&p_full[x], j & 1);
-        if (x == 0) mbar_wait(&v_full[stage], (j / ST) & 1u);
+        if (tr && j < 64) tr[8 * j + 1] = clock64();
         tc_fence_after();
-        const uint32_t pa0 = p_addr + x * 2 * kChunkBytes;
+        issue_qk(j + 1);
+        if (tr && j < 64) tr[8 * j + 2] = clock64();
+      }
+      mbar_wait(&p_full[x], j & 1);
+      if (tr && j < 64) tr[8 * j + 3] = clock64();
+      mbar_wait(&v_full[stage], (j / ST) & 1u);
+      if (tr && j < 64) tr[8 * j + 4] = clock64();
+      tc_fence_after();
+      const uint32_t v_addr = smem_u32(sV + stage * Cfg::kTile);
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
           const uint32_t pa = pa0 + (ks >> 2) * kChunkBytes + (ks & 3) * 32;
-          umma_ss(tmem_base + 256 + x * 128, make_smem_desc_sw128(pa, 16, 1024),
-                  make_smem_desc_sw128(v_addr + ks * 2048, kChunkBytes, 1024), idesc_pv, (j | ks) != 0 ? 1u : 0u);
+          umma_ss(tO, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(v_addr + ks * 2048, kChunkBytes, 1024),
+                  idesc_pv, (j | ks) != 0 ? 1u : 0u);
         }
-        if (x == 1) tc_commit(&v_empty[stage]);  // both query tiles are done with V[j]
+        tc_commit(&v_empty[stage]);  // released once both query tiles are done with V[j]
         tc_commit(&o_done[x]);
       }
+      __syncwarp();
+      if (tr && j < 64) tr[8 * j + 5] = clock64();
     }
    }
   } else {
@@ -198,14 +213,21 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int sw = r & 7;
     const float sc = a.scale_log2;
     float m_ref = 0.f, l = 0.f;
+    long long* tr = (a.trace && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+                        ? a.trace + (x * 4 + ew) * 512
+                        : nullptr;
+    const bool early = (a.variant & 4) == 0;
+#define MIMO_TR(k) if (tr && j < 64) tr[j * 8 + (k)] = clock64()
     for (int j = 0; j < T; ++j) {
       const bool bank = j >= a.n_self_tiles;
       const int len = bank ? a.lb : a.lq;
       const int row0 = (bank ? j - a.n_self_tiles : j) * BKV;
       int valid = len - row0;
       if (valid > BKV) valid = BKV;
+      MIMO_TR(0);
       mbar_wait(&s_full[x], j & 1);
       tc_fence_after();
+      MIMO_TR(1);
       // ---- the whole row of S -> registers, then hand S_X back to the tensor pipe ----
       uint32_t sv[4][32];
       tmem_ld_x32(tS, sv[0]);
@@ -216,6 +238,7 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[x]);
+      MIMO_TR(2);
       // ---- tile maximum (4 independent chains) ----
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
       if (valid == BKV) {
@@ -248,12 +271,17 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           l *= alpha;
         }
       }
-      // ---- probabilities -> swizzled smem ----
+      // The two groups share one MUFU pipe per SM sub-partition. Started together they stay in lockstep - both in
+      // their exponentials (each at half rate), then both in their MUFU-free part - so B is held back once, by
+      // the length of A's first exponential phase, and from then on one group's loads / stores / waits hide under
+      // the other's exponentials.
+      if (j == 0 && x == 1 && !(a.variant & 8)) mbar_wait(stagger, 0);
+      // ---- probabilities (packed in registers) ----
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       const float nm = -m_ref;
+      uint32_t pk[64];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i]), sc, nm));
@@ -264,22 +292,49 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           s1 += p1;
           s2 += p2;
           s3 += p3;
-          pk[i] = C::pack(p0, p1);
-          pk[i + 1] = C::pack(p2, p3);
+          pk[c * 16 + i] = C::pack(p0, p1);
+          pk[c * 16 + i + 1] = C::pack(p2, p3);
         }
-        // P_X (and O_X) may only be overwritten once the previous P_X.V has retired
-        if (c == 0 && j > 0) {
-          mbar_wait(&o_done[x], (j - 1) & 1);
-          tc_fence_after();
+        if (c == 3 && j == 0 && x == 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(stagger);
         }
+        if (early) {
+          if (c == 0 && j > 0) {
+            MIMO_TR(3);
+            mbar_wait(&o_done[x], (j - 1) & 1);
+            tc_fence_after();
+            MIMO_TR(4);
+          }
+          uint8_t* line = prow + (c >> 1) * kChunkBytes;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int piece = (c & 1) * 4 + q;
+            *reinterpret_cast<uint4*>(line + ((piece ^ sw) << 4)) =
+                make_uint4(pk[c * 16 + 4 * q], pk[c * 16 + 4 * q + 1], pk[c * 16 + 4 * q + 2], pk[c * 16 + 4 * q + 3]);
+          }
+        }
+      }
+      // P_X (and O_X) may only be overwritten once the previous P_X.V has retired - by now it has, the wait is free
+      if (!early) {
+      if (j > 0) {
+        MIMO_TR(3);
+        mbar_wait(&o_done[x], (j - 1) & 1);
+        tc_fence_after();
+        MIMO_TR(4);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
         uint8_t* line = prow + (c >> 1) * kChunkBytes;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int piece = (c & 1) * 4 + q;
           *reinterpret_cast<uint4*>(line + ((piece ^ sw) << 4)) =
-              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              make_uint4(pk[c * 16 + 4 * q], pk[c * 16 + 4 * q + 1], pk[c * 16 + 4 * q + 2], pk[c * 16 + 4 * q + 3]);
         }
       }
+      }
+      MIMO_TR(5);
       l += (s0 + s1) + (s2 + s3);
       // ---- correction of O (rare) ----
       if (rescale) {
@@ -295,7 +350,9 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&p_full[x]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);
+      MIMO_TR(6);
     }
     // ---- epilogue: O / l -> global ----
     mbar_wait(&o_done[x], (T - 1) & 1);

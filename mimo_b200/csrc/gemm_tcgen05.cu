@@ -93,7 +93,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::kBarBytes);  // [2][256]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int num_tiles = num_m_tiles * num_n_tiles;
 
@@ -123,7 +123,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // tile -> coordinates of its first output row / pixel
   auto tile_origin = [&](int m_tile, int& x0, int& y0, int& n0) {
@@ -136,7 +136,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
   };
 
-  if (warp == 0 && lane == 0) {
+  // Producer and issuer warps run their loops with all 32 lanes (uniform control flow) and elect one lane for the
+  // TMA / tcgen05 instructions: addresses and descriptors then live in uniform registers. A lane-0-only branch makes
+  // the compiler treat them as divergent and wrap every instruction in a ~20-instruction election loop - ~150 clk per
+  // MMA, more than a 128x256x16 MMA takes.
+  if (warp == 0) {
     // ===================== TMA producer (operands) =====================
     uint32_t it = 0;
     const int kb_per_tap = g.kb0 + g.kb1;
@@ -151,6 +155,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + BM * BK * 2;
+        if (elect_one()) {
         if (!g.conv) {
           mbar_expect_tx(&full_bar[stage], BM * BK * 2 + BN * BK * 2);
           if (kb < g.kb0) {  // A = [A0 | A1] along K (virtual concat for the up-block shortcut GEMMs)
@@ -175,9 +180,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           }
           tma_load_2d(sb, &tmB, &full_bar[stage], kcoord, n_tile * BN);
         }
+        }
+        __syncwarp();
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_f16(BM, BN, kBf16, false, false);
     uint32_t it = 0, lt = 0;
@@ -196,16 +203,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const uint32_t sb = sa + BM * BK * 2;
         const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
         const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
-          umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
+            umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          if (kb == num_k_blocks - 1) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         }
-        tc_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+        __syncwarp();
       }
-      tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
     }
-  } else if (warp == 3 && lane == 0) {
+  } else if (warp == 3) {
     // ===================== TMA producer (residual chunks) =====================
     if constexpr (kRes) {
       // Each epilogue column group owns half of the slots as a private ring (a barrier shared by consumers that can
@@ -226,12 +236,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const uint32_t k = cnt[h]++;
             const uint32_t slot = h * SH + k % SH;
             mbar_wait(&res_empty[slot], ((k / SH) & 1u) ^ 1u);
-            mbar_expect_tx(&res_full[slot], g.chunk_bytes);
-            const int col = n_tile * BN + c * 32;  // boxes beyond N are zero-filled (keeps the slot sequence uniform)
-            if (g.conv)
-              tma_load_4d(sRes + slot * kChunk, &tmRes, &res_full[slot], col, x0, y0, n0);
-            else
-              tma_load_2d(sRes + slot * kChunk, &tmRes, &res_full[slot], col, m_tile * BM);
+            if (elect_one()) {
+              mbar_expect_tx(&res_full[slot], g.chunk_bytes);
+              const int col = n_tile * BN + c * 32;  // boxes beyond N are zero-filled (keeps the slot sequence uniform)
+              if (g.conv)
+                tma_load_4d(sRes + slot * kChunk, &tmRes, &res_full[slot], col, x0, y0, n0);
+              else
+                tma_load_2d(sRes + slot * kChunk, &tmRes, &res_full[slot], col, m_tile * BM);
+            }
+            __syncwarp();
           }
         }
       }

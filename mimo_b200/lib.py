@@ -121,7 +121,8 @@ SYMBOLS = {
     "mimo_cfg_ddim_step": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _I64, _F, _F, _F, _F, _F, _I32, _VP]),
 }
 # test hook, not part of the public header
-_DEBUG_SYMBOLS = {"mimo_debug_force_bn": (C.c_int, [C.c_int]), "mimo_debug_attn_variant": (C.c_int, [C.c_int])}
+_DEBUG_SYMBOLS = {"mimo_debug_force_bn": (C.c_int, [C.c_int]), "mimo_debug_attn_variant": (C.c_int, [C.c_int]),
+                  "mimo_debug_attn_trace": (C.c_int, [C.c_void_p])}
 
 _lib = None
 

@@ -16,7 +16,7 @@ from mimo_b200 import ops  # noqa: E402
 dev = "cuda"
 
 
-def attn(n=4, lq=4096, d=40, lb=4096):
+def attn(n=12, lq=4096, d=40, lb=4096):
     C = 8 * d
     qkv = torch.randn(n * lq, 3 * C, device=dev).half()
     bkv = torch.randn(2, lb, 2 * C, device=dev).half()
