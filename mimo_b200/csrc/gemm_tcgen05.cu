@@ -19,6 +19,8 @@
 // the K tail, and the output / residual boxes use the same {TW, TH, TN} footprint (stores are clipped at image
 // borders). Two source tensors give the up-blocks' channel concat without materialising it.
 #include <cuda_runtime.h>
+
+#include <type_traits>
 #include <cudaTypedefs.h>
 
 #include "../../include/mimo_b200.h"
@@ -39,6 +41,7 @@ struct EpiArgs {
   long long ld_rowvec;
   float scale;
   int act;
+  long long* trace;  // debug (mimo_debug_gemm_trace): clock64 timeline of CTA 0, or nullptr
 };
 
 struct ConvGeom {
@@ -153,6 +156,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const uint32_t stage = it % Cfg::kStages;
         const uint32_t phase = (it / Cfg::kStages) & 1u;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (ep.trace && blockIdx.x == 0 && lane == 0 && it < 512) ep.trace[2560 + it] = clock64();
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + BM * BK * 2;
         if (elect_one()) {
@@ -193,12 +197,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const uint32_t acc_phase = (lt >> 1) & 1u;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
       tc_fence_after();
+      long long* trm = (ep.trace && blockIdx.x == 0 && lane == 0 && lt < 32) ? ep.trace + 2048 + lt * 16 : nullptr;
+      if (trm) trm[0] = clock64();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
         const uint32_t stage = it % Cfg::kStages;
         const uint32_t phase = (it / Cfg::kStages) & 1u;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (trm && kb < 12) trm[1 + kb] = clock64();
         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint32_t sb = sa + BM * BK * 2;
         const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
@@ -214,6 +221,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
         __syncwarp();
       }
+      if (trm) trm[14] = clock64();
     }
   } else if (warp == 3) {
     // ===================== TMA producer (residual chunks) =====================
@@ -261,8 +269,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     uint8_t* obuf_base = sOut + hsel * 2 * kChunk;
     const int bar_id = 2 + hsel;
     constexpr int H0 = (NCHUNK + 1) / 2;
+    const bool do_silu = ep.act == MIMO_ACT_SILU;
     uint32_t lt = 0, oc = 0, rc = 0;
+    long long* tr = (ep.trace && blockIdx.x == 0 && ew == 0 && lane == 0) ? ep.trace + hsel * 1024 : nullptr;
+    int tk = 0;
+#define GEMM_TR() do { if (tr && lt < 32 && tk < 32) tr[lt * 32 + tk++] = clock64(); } while (0)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      tk = 0;
+      GEMM_TR();  // 0: tile start
       const int m_tile = tile / num_n_tiles;
       const int n_tile = tile % num_n_tiles;
       const uint32_t acc = lt & 1u;
@@ -270,131 +284,170 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int x0, y0, n0;
       tile_origin(m_tile, x0, y0, n0);
 
-      // ---- per-tile column constants -> smem: bias (+ the per-branch vector when the whole tile shares one group) ----
-      long long grp_first, grp_last, row = 0;
+      // ---- rows of this tile; which group(s) of the per-branch vector they belong to ----
+      // (32-bit arithmetic: M, the pixel count and rows_per_group all fit an int; 64-bit divisions cost ~1 us here)
+      const uint32_t rpg = static_cast<uint32_t>(ep.rows_per_group);
+      long long row = 0;
       bool row_ok = true;
       if (!g.conv) {
-        const long long m0 = static_cast<long long>(m_tile) * BM;
-        long long m1 = m0 + BM - 1;
-        if (m1 > M - 1) m1 = M - 1;
-        grp_first = m0 / ep.rows_per_group;
-        grp_last = m1 / ep.rows_per_group;
-        row = m0 + r;
+        row = static_cast<long long>(m_tile) * BM + r;
         row_ok = row < M;
       } else {
-        int n1 = n0 + g.TN - 1;
-        if (n1 > g.NI - 1) n1 = g.NI - 1;
-        grp_first = (static_cast<long long>(n0) * g.H * g.W) / ep.rows_per_group;
-        grp_last = (static_cast<long long>(n1 + 1) * g.H * g.W - 1) / ep.rows_per_group;
         const int x = r % g.TW, y = (r / g.TW) % g.TH, n = r / (g.TW * g.TH);
         row_ok = (n < g.TN) && (x0 + x < g.W) && (y0 + y < g.H) && (n0 + n < g.NI);
         row = (static_cast<long long>(n0 + n) * g.H + (y0 + y)) * g.W + (x0 + x);
       }
-      const bool rv_uniform = ep.rowvec != nullptr && grp_first == grp_last;
-      float* sb = sbias + acc * 256;
-      {
-        const int e = (warp - 4) * 32 + lane;
-        for (int j = e; j < BN; j += 256) {
-          const int col = n_tile * BN + j;
-          float v = 0.f;
-          if (col < N) {
-            if (ep.bias) v = C::to_f(static_cast<const T*>(ep.bias)[col]);
-            if (rv_uniform) v += C::to_f(static_cast<const T*>(ep.rowvec)[grp_first * ep.ld_rowvec + col]);
-          }
-          sb[j] = v;
+      // first / last group touched by a tile (uniform per tile)
+      auto tile_groups = [&](int mt, uint32_t& gf, uint32_t& gl) {
+        if (!g.conv) {
+          const uint32_t m0 = static_cast<uint32_t>(mt) * BM;
+          uint32_t m1 = m0 + BM - 1;
+          if (m1 > static_cast<uint32_t>(M) - 1) m1 = static_cast<uint32_t>(M) - 1;
+          gf = m0 / rpg;
+          gl = m1 / rpg;
+        } else {
+          int tx, ty, tn;
+          tile_origin(mt, tx, ty, tn);
+          int n1 = tn + g.TN - 1;
+          if (n1 > g.NI - 1) n1 = g.NI - 1;
+          const uint32_t hw = static_cast<uint32_t>(g.H) * g.W;
+          gf = (static_cast<uint32_t>(tn) * hw) / rpg;
+          gl = (static_cast<uint32_t>(n1 + 1) * hw - 1) / rpg;
         }
+      };
+      // column constants of a tile: bias (+ the per-branch vector when the whole tile shares one group)
+      const int ce = (warp - 4) * 32 + lane;  // one column per epilogue thread (BN <= 256)
+      auto load_consts = [&](int t) -> float {
+        float v = 0.f;
+        const int mt = t / num_n_tiles, nt = t % num_n_tiles;
+        const int col = nt * BN + ce;
+        if (ce < BN && col < N) {
+          if (ep.bias) v = C::to_f(static_cast<const T*>(ep.bias)[col]);
+          if (ep.rowvec) {
+            uint32_t gf, gl;
+            tile_groups(mt, gf, gl);
+            if (gf == gl) v += C::to_f(static_cast<const T*>(ep.rowvec)[static_cast<long long>(gf) * ep.ld_rowvec + col]);
+          }
+        }
+        return ep.act == MIMO_ACT_GEGLU ? v : v * ep.scale;  // y = acc * scale + (bias + vec) * scale
+      };
+      bool rv_uniform = false;
+      if (ep.rowvec) {
+        uint32_t gf, gl;
+        tile_groups(m_tile, gf, gl);
+        rv_uniform = gf == gl;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+      float* sb = sbias + acc * 256;
+      if (lt == 0 && ce < BN) sb[ce] = load_consts(tile);  // later tiles: staged at the end of the previous tile
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only: constants visible, previous tile retired
+      GEMM_TR();  // 1: column constants staged
+      // constants of the next tile: the loads fly under this tile's chunks
+      const int next_tile = tile + gridDim.x;
+      float next_const = 0.f;
+      if (next_tile < num_tiles) next_const = load_consts(next_tile);
       const T* rv = (ep.rowvec && !rv_uniform && row_ok)
-                        ? static_cast<const T*>(ep.rowvec) + (row / ep.rows_per_group) * ep.ld_rowvec
+                        ? static_cast<const T*>(ep.rowvec) + static_cast<long long>(static_cast<uint32_t>(row) / rpg) * ep.ld_rowvec
                         : nullptr;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      GEMM_TR();  // 2: accumulator ready
 
       if (ep.act != MIMO_ACT_GEGLU) {
         const int cbase = hsel ? H0 : 0;
         const int ccount = hsel ? NCHUNK - H0 : H0;
-#pragma unroll
-        for (int i = 0; i < H0; ++i) {
-          if (i < ccount) {
-            const int c = cbase + i;
-            uint8_t* obuf = obuf_base + (oc & 1u) * kChunk;
-            ++oc;
-            if (issuer) tma_store_wait_read0();  // see "Staging-buffer reuse" below
-            uint32_t v[32];
-            tmem_ld_x32(taddr + c * 32, v);
-            const uint8_t* rrow = nullptr;
-            uint32_t rslot = 0;
-            if constexpr (kRes) {
-              constexpr int SH = Cfg::kResSlots / 2;
-              const uint32_t k = rc++;
-              rslot = hsel * SH + k % SH;
-              mbar_wait(&res_full[rslot], (k / SH) & 1u);
-              rrow = sRes + rslot * kChunk + r * 64;
-            }
-            tmem_ld_wait();
-            const int col0 = n_tile * BN + c * 32;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float f[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8 + 4);
-              f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x;
-              f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
-              f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z;
-              f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
-              f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x;
-              f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
-              f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z;
-              f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
-              if (rv && col0 + q * 8 < N) {
-                const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + col0 + q * 8));
-                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 t = C::unpack(bw[j]);
-                  f[2 * j] += t.x;
-                  f[2 * j + 1] += t.y;
-                }
-              }
-              if constexpr (kRes) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(rrow + ((q ^ sw) << 4));
-                const uint32_t bw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 t = C::unpack(bw[j]);
-                  f[2 * j] += t.x;
-                  f[2 * j + 1] += t.y;
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                f[j] *= ep.scale;
-                if (ep.act == MIMO_ACT_SILU) f[j] = silu_f(f[j]);
-              }
-              uint4 o;
-              o.x = C::pack(f[0], f[1]);
-              o.y = C::pack(f[2], f[3]);
-              o.z = C::pack(f[4], f[5]);
-              o.w = C::pack(f[6], f[7]);
-              *reinterpret_cast<uint4*>(obuf + r * 64 + ((q ^ sw) << 4)) = o;
-            }
-            if constexpr (kRes) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&res_empty[rslot]);
-            }
-            fence_proxy_async_smem();
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-            if (issuer) {
-              if (g.conv)
-                tma_store_4d(&tmOut, obuf, col0, x0, y0, n0);
-              else
-                tma_store_2d(&tmOut, obuf, col0, m_tile * BM);
-              tma_store_commit();
-            }
+        const float scale = ep.scale;
+        // one 32-column chunk; the activation is a compile-time tag so the element loop is branch-free
+        auto chunk = [&](int c, auto silu_tag) {
+          constexpr bool kSilu = decltype(silu_tag)::value;
+          uint8_t* obuf = obuf_base + (oc & 1u) * kChunk;
+          ++oc;
+          GEMM_TR();  // chunk +0
+          uint32_t v[32];
+          tmem_ld_x32(taddr + c * 32, v);
+          [[maybe_unused]] const uint8_t* rrow = nullptr;
+          [[maybe_unused]] uint32_t rslot = 0;
+          if constexpr (kRes) {
+            constexpr int SH = Cfg::kResSlots / 2;
+            const uint32_t k = rc++;
+            rslot = hsel * SH + k % SH;
+            mbar_wait(&res_full[rslot], (k / SH) & 1u);
+            rrow = sRes + rslot * kChunk + r * 64;
           }
+          tmem_ld_wait();
+          GEMM_TR();  // chunk +1: accumulators (and residual) in registers
+          const int col0 = n_tile * BN + c * 32;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8 + 4);
+            f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), scale, b0.x);
+            f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), scale, b0.y);
+            f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), scale, b0.z);
+            f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), scale, b0.w);
+            f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), scale, b1.x);
+            f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), scale, b1.y);
+            f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), scale, b1.z);
+            f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), scale, b1.w);
+            if (rv && col0 + q * 8 < N) {  // tile straddles groups of the per-branch vector (rare)
+              const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + col0 + q * 8));
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 t = C::unpack(bw[j]);
+                f[2 * j] = fmaf(t.x, scale, f[2 * j]);
+                f[2 * j + 1] = fmaf(t.y, scale, f[2 * j + 1]);
+              }
+            }
+            if constexpr (kRes) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(rrow + ((q ^ sw) << 4));
+              const uint32_t bw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 t = C::unpack(bw[j]);
+                f[2 * j] = fmaf(t.x, scale, f[2 * j]);
+                f[2 * j + 1] = fmaf(t.y, scale, f[2 * j + 1]);
+              }
+            }
+            if constexpr (kSilu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+            }
+            uint4 o;
+            o.x = C::pack(f[0], f[1]);
+            o.y = C::pack(f[2], f[3]);
+            o.z = C::pack(f[4], f[5]);
+            o.w = C::pack(f[6], f[7]);
+            *reinterpret_cast<uint4*>(obuf + r * 64 + ((q ^ sw) << 4)) = o;
+          }
+          if constexpr (kRes) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&res_empty[rslot]);
+          }
+          GEMM_TR();  // chunk +2: staged
+          fence_proxy_async_smem();
+          if (issuer) tma_store_wait_read0();  // see "Staging-buffer reuse" below
+          GEMM_TR();  // chunk +3: fenced, previous store has left shared memory
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          GEMM_TR();  // chunk +4: group barrier
+          if (issuer) {
+            if (g.conv)
+              tma_store_4d(&tmOut, obuf, col0, x0, y0, n0);
+            else
+              tma_store_2d(&tmOut, obuf, col0, m_tile * BM);
+            tma_store_commit();
+          }
+        };
+        // not unrolled: the per-tile code has to stay resident in the instruction cache (fully unrolled, with the
+        // activation / row-vector variants, it was ~80 KB and every warp crawled at ~6 clk per instruction)
+        if (do_silu) {
+#pragma unroll 1
+          for (int i = 0; i < ccount; ++i) chunk(cbase + i, std::true_type{});
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < ccount; ++i) chunk(cbase + i, std::false_type{});
         }
       } else {
         // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates; 32-column pairs are split
@@ -404,13 +457,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         constexpr int P0 = (NPAIR + 1) / 2;
         const int pbase = hsel ? P0 : 0;
         const int pcount = hsel ? NPAIR - P0 : P0;
-#pragma unroll
-        for (int i = 0; i < P0; ++i) {
-          if (i < pcount) {
+#pragma unroll 1
+        for (int i = 0; i < pcount; ++i) {
+          {
             const int c = pbase + i;
             uint8_t* obuf = obuf_base + (oc & 1u) * kChunk;
             ++oc;
-            if (issuer) tma_store_wait_read0();
             uint32_t v[32], gt[32];
             tmem_ld_x32(taddr + c * 32, v);
             tmem_ld_x32(taddr + HALF + c * 32, gt);
@@ -432,6 +484,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               *reinterpret_cast<uint4*>(obuf + r * 64 + ((q ^ sw) << 4)) = o;
             }
             fence_proxy_async_smem();
+            if (issuer) tma_store_wait_read0();
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             if (issuer) {
               tma_store_2d(&tmOut, obuf, n_tile * HALF + c * 32, m_tile * BM);
@@ -440,6 +493,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           }
         }
       }
+      if (next_tile < num_tiles && ce < BN) sbias[(acc ^ 1u) * 256 + ce] = next_const;
       // all TMEM reads of this accumulator buffer are complete (wait::ld above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -457,9 +511,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 }
 
 // Staging-buffer reuse: a group's two 8 KiB buffers alternate per chunk. The issuer executes
-// cp.async.bulk.wait_group.read 0 at the START of chunk i, i.e. after it committed store(i-1) and before it joins
-// barrier(i); every thread writes buffer (i+1)&1 only after barrier(i), by which time stores <= i-1 — including
-// store(i-1), the last reader of that buffer — have finished reading shared memory.
+// cp.async.bulk.wait_group.read 0 just BEFORE it joins barrier(i) - after its own math of chunk i, so the ~700 clk a
+// store needs to drain shared memory hide under that math - i.e. after it committed store(i-1); every thread writes
+// buffer (i+1)&1 only after barrier(i), by which time stores <= i-1 - including store(i-1), the last reader of that
+// buffer - have finished reading shared memory.
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -500,6 +555,9 @@ static int launch_bn(int bn, bool res, const Maps& m, int M, int N, int mt, int 
     case 160:
       return res ? launch_cfg<160, kBf16, true>(m, M, N, mt, nt, nkb, g, ep, st)
                  : launch_cfg<160, kBf16, false>(m, M, N, mt, nt, nkb, g, ep, st);
+    case 192:
+      return res ? launch_cfg<192, kBf16, true>(m, M, N, mt, nt, nkb, g, ep, st)
+                 : launch_cfg<192, kBf16, false>(m, M, N, mt, nt, nkb, g, ep, st);
     case 256:
       return res ? launch_cfg<256, kBf16, true>(m, M, N, mt, nt, nkb, g, ep, st)
                  : launch_cfg<256, kBf16, false>(m, M, N, mt, nt, nkb, g, ep, st);
@@ -507,7 +565,8 @@ static int launch_bn(int bn, bool res, const Maps& m, int M, int N, int mt, int 
   return set_error(MIMO_ERR_ARG, "gemm: unsupported BN");
 }
 
-static int g_force_bn = 0;  // test hook (mimo_debug_force_bn)
+static int g_force_bn = 0;
+static long long* g_gemm_trace = nullptr;  // test hook (mimo_debug_gemm_trace)
 
 // Tile-width choice: least padded columns first, then the widest tile (fewer A re-reads, higher MMA N).
 int pick_bn(int N, bool geglu, long long m_tiles) {
@@ -517,10 +576,10 @@ int pick_bn(int N, bool geglu, long long m_tiles) {
     if (N % 128 == 0) return 128;
     return 64;
   }
-  const int cands[4] = {256, 160, 128, 64};
+  const int cands[5] = {256, 192, 160, 128, 64};
   int best = 64;
   double best_eff = -1.0;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
     const int nt = (N + bn - 1) / bn;
     double eff = static_cast<double>(N) / (static_cast<double>(nt) * bn);
@@ -540,9 +599,11 @@ static EpiArgs make_epi(const mimo_epilogue& e, int N) {
   a.bias = e.bias;
   a.rowvec = e.rowvec;
   a.rows_per_group = e.rows_per_group > 0 ? e.rows_per_group : 1;
+  if (a.rows_per_group > 0x7fffffffLL) a.rows_per_group = 0x7fffffffLL;  // row counts are ints: same grouping
   a.ld_rowvec = e.ld_rowvec > 0 ? e.ld_rowvec : N;
   a.scale = e.scale;
   a.act = e.act;
+  a.trace = g_gemm_trace;
   return a;
 }
 
@@ -552,6 +613,10 @@ using namespace mimo;
 
 extern "C" int mimo_debug_force_bn(int bn) {
   g_force_bn = bn;
+  return 0;
+}
+extern "C" int mimo_debug_gemm_trace(void* buf) {  // >= 4096 int64 of device memory, or NULL
+  g_gemm_trace = static_cast<long long*>(buf);
   return 0;
 }
 

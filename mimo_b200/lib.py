@@ -122,7 +122,8 @@ SYMBOLS = {
 }
 # test hook, not part of the public header
 _DEBUG_SYMBOLS = {"mimo_debug_force_bn": (C.c_int, [C.c_int]), "mimo_debug_attn_variant": (C.c_int, [C.c_int]),
-                  "mimo_debug_attn_trace": (C.c_int, [C.c_void_p])}
+                  "mimo_debug_attn_trace": (C.c_int, [C.c_void_p]),
+                  "mimo_debug_gemm_trace": (C.c_int, [C.c_void_p])}
 
 _lib = None
 

@@ -88,6 +88,7 @@ def gemm_shapes():
     ok = True
     for (M, N, K, bn) in [(128, 64, 128, 64), (128, 64, 16, 64), (128, 64, 200, 64), (100, 64, 64, 64),
                           (256, 128, 320, 128), (384, 320, 320, 160), (256, 512, 256, 256), (300, 200, 136, 0),
+                          (384, 960, 320, 192), (200, 400, 72, 192),
                           (2, 1280, 320, 0), (4096, 320, 320, 0), (4096, 2560, 320, 0), (1000, 640, 2560, 0)]:
         ok &= gemm_case(M, N, K, bn)[0]
     return ok
@@ -97,6 +98,7 @@ def gemm_persistent():
     # more tiles than SMs -> exercises the accumulator double buffering and barrier phase wrap-around
     ok = True
     for (M, N, K, bn) in [(128 * 300, 64, 64, 64), (128 * 160, 320, 192, 160), (128 * 40, 1280, 1280, 256),
+                          (128 * 100, 960, 320, 192),
                           (128 * 151, 128, 64 * 13, 128)]:
         ok &= gemm_case(M, N, K, bn)[0]
     return ok

@@ -39,6 +39,13 @@ def gemm(M=196608, N=320, K=320):
         ops.gemm(a, w, bias=b, residual=r)
 
 
+def qkv(M=196608, N=960, K=320):
+    a = torch.randn(M, K, device=dev).half()
+    w = torch.randn(N, K, device=dev).half()
+    for _ in range(4):
+        ops.gemm(a, w)
+
+
 def geglu(M=196608, N=2560, K=320):
     a = torch.randn(M, K, device=dev).half()
     w = torch.randn(N, K, device=dev).half()
