@@ -359,13 +359,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const int ccount = hsel ? NCHUNK - H0 : H0;
         const float scale = ep.scale;
         // one 32-column chunk; the activation is a compile-time tag so the element loop is branch-free
-        auto chunk = [&](int c, auto silu_tag) {
+        // kMode 0: no column constants, unit scale, no residual -> accumulators are packed as they are;
+        //       1: y = acc * scale + consts (+ residual);  2: as 1, plus per-row vectors (tile straddles groups)
+        auto chunk = [&](int c, auto silu_tag, auto mode_tag) {
           constexpr bool kSilu = decltype(silu_tag)::value;
+          constexpr int kMode = decltype(mode_tag)::value;
           uint8_t* obuf = obuf_base + (oc & 1u) * kChunk;
           ++oc;
           GEMM_TR();  // chunk +0
           uint32_t v[32];
           tmem_ld_x32(taddr + c * 32, v);
+          float4 cb[8];
+          if constexpr (kMode != 0) {  // constants land in registers while the TMEM load is in flight
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cb[q] = *reinterpret_cast<const float4*>(sb + c * 32 + q * 4);
+          }
           [[maybe_unused]] const uint8_t* rrow = nullptr;
           [[maybe_unused]] uint32_t rslot = 0;
           if constexpr (kRes) {
@@ -381,24 +389,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float f[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(sb + c * 32 + q * 8 + 4);
-            f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), scale, b0.x);
-            f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), scale, b0.y);
-            f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), scale, b0.z);
-            f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), scale, b0.w);
-            f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), scale, b1.x);
-            f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), scale, b1.y);
-            f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), scale, b1.z);
-            f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), scale, b1.w);
-            if (rv && col0 + q * 8 < N) {  // tile straddles groups of the per-branch vector (rare)
-              const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + col0 + q * 8));
-              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+            if constexpr (kMode == 0) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 t = C::unpack(bw[j]);
-                f[2 * j] = fmaf(t.x, scale, f[2 * j]);
-                f[2 * j + 1] = fmaf(t.y, scale, f[2 * j + 1]);
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+            } else {
+              const float4 b0 = cb[2 * q], b1 = cb[2 * q + 1];
+              f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), scale, b0.x);
+              f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), scale, b0.y);
+              f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), scale, b0.z);
+              f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), scale, b0.w);
+              f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), scale, b1.x);
+              f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), scale, b1.y);
+              f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), scale, b1.z);
+              f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), scale, b1.w);
+            }
+            if constexpr (kMode == 2) {
+              if (rv && col0 + q * 8 < N) {
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + col0 + q * 8));
+                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 t = C::unpack(bw[j]);
+                  f[2 * j] = fmaf(t.x, scale, f[2 * j]);
+                  f[2 * j + 1] = fmaf(t.y, scale, f[2 * j + 1]);
+                }
               }
             }
             if constexpr (kRes) {
@@ -440,14 +454,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             tma_store_commit();
           }
         };
+        using M0 = std::integral_constant<int, 0>;
+        using M1 = std::integral_constant<int, 1>;
+        using M2 = std::integral_constant<int, 2>;
+        const bool need_rv = ep.rowvec != nullptr && !rv_uniform;  // uniform per tile
+        const bool plain = !kRes && !do_silu && !need_rv && ep.bias == nullptr && ep.rowvec == nullptr && scale == 1.0f;
         // not unrolled: the per-tile code has to stay resident in the instruction cache (fully unrolled, with the
         // activation / row-vector variants, it was ~80 KB and every warp crawled at ~6 clk per instruction)
-        if (do_silu) {
+        if (plain) {
 #pragma unroll 1
-          for (int i = 0; i < ccount; ++i) chunk(cbase + i, std::true_type{});
+          for (int i = 0; i < ccount; ++i) chunk(cbase + i, std::false_type{}, M0{});
+        } else if (need_rv) {
+          if (do_silu) {
+#pragma unroll 1
+            for (int i = 0; i < ccount; ++i) chunk(cbase + i, std::true_type{}, M2{});
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < ccount; ++i) chunk(cbase + i, std::false_type{}, M2{});
+          }
+        } else if (do_silu) {
+#pragma unroll 1
+          for (int i = 0; i < ccount; ++i) chunk(cbase + i, std::true_type{}, M1{});
         } else {
 #pragma unroll 1
-          for (int i = 0; i < ccount; ++i) chunk(cbase + i, std::false_type{});
+          for (int i = 0; i < ccount; ++i) chunk(cbase + i, std::false_type{}, M1{});
         }
       } else {
         // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates; 32-column pairs are split
