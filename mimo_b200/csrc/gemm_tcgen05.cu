@@ -31,7 +31,13 @@ namespace mimo {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = one 128-byte swizzle row
-constexpr int kGemmThreads = 384;
+constexpr int kEpiGroups = 3;                        // epilogue warpgroups (4 warps each), splitting a tile's chunks
+constexpr int kGemmThreads = 128 + kEpiGroups * 128;  // warps 0-3: TMA / MMA / TMEM / residual; then the epilogue
+// chunk range of epilogue group g when n chunks are dealt out as evenly as possible
+__host__ __device__ constexpr int grp_count(int n, int g) { return n / kEpiGroups + (g < n % kEpiGroups ? 1 : 0); }
+__host__ __device__ constexpr int grp_base(int n, int g) {
+  return g * (n / kEpiGroups) + (g < n % kEpiGroups ? g : n % kEpiGroups);
+}
 constexpr int kChunk = 8192;  // one 128-row x 32-column (64 B) epilogue chunk
 
 struct EpiArgs {
@@ -60,8 +66,9 @@ template <int BN, bool kRes>
 struct GemmCfg {
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
   static constexpr int kNChunk = BN / 32;
-  static constexpr int kOutBytes = 2 * 2 * kChunk;  // two warp groups x double buffer
-  static constexpr int kResSlots = kRes ? (BN >= 256 ? 4 : (2 * kNChunk < 8 ? 2 * kNChunk : 8)) : 0;
+  static constexpr int kOutBytes = kEpiGroups * 2 * kChunk;  // per epilogue group: double buffer
+  static constexpr int kResPerGroup = BN >= 256 ? 1 : 2;  // private ring of each epilogue group
+  static constexpr int kResSlots = kRes ? kEpiGroups * kResPerGroup : 0;
   static constexpr int kResBytes = kResSlots * kChunk;
   static constexpr int kBarBytes = 512;
   static constexpr int kFixed = kBarBytes + 2048 /*sbias*/ + kOutBytes + kResBytes;
@@ -114,7 +121,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 8);
+      mbar_init(&tmem_empty[b], kEpiGroups * 4);
     }
     for (int s = 0; s < Cfg::kResSlots; ++s) {
       mbar_init(&res_full[s], 1);
@@ -145,53 +152,63 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   // MMA, more than a 128x256x16 MMA takes.
   if (warp == 0) {
     // ===================== TMA producer (operands) =====================
-    uint32_t it = 0;
+    // (all index arithmetic is incremental: this warp has ~300 clk per k-block and runs at ~5 clk per instruction
+    // next to the epilogue warps of its sub-partition - divisions here used to throttle the 3x3 convolutions)
+    uint32_t it = 0, stage = 0, phase = 0;
     const int kb_per_tap = g.kb0 + g.kb1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / num_n_tiles;
       const int n_tile = tile % num_n_tiles;
       int x0, y0, n0;
       tile_origin(m_tile, x0, y0, n0);
+      int rem = 0, dx = -1, dy = -1, tap_k = 0;  // conv: k-block inside the tap, tap offsets, tap * ctot
       for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-        const uint32_t stage = it % Cfg::kStages;
-        const uint32_t phase = (it / Cfg::kStages) & 1u;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (ep.trace && blockIdx.x == 0 && lane == 0 && it < 512) ep.trace[2560 + it] = clock64();
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + BM * BK * 2;
         if (elect_one()) {
-        if (!g.conv) {
-          mbar_expect_tx(&full_bar[stage], BM * BK * 2 + BN * BK * 2);
-          if (kb < g.kb0) {  // A = [A0 | A1] along K (virtual concat for the up-block shortcut GEMMs)
-            tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, m_tile * BM);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
+          if (!g.conv) {
+            mbar_expect_tx(&full_bar[stage], BM * BK * 2 + BN * BK * 2);
+            if (kb < g.kb0) {  // A = [A0 | A1] along K (virtual concat for the up-block shortcut GEMMs)
+              tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, m_tile * BM);
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
+            } else {
+              tma_load_2d(sa, &tmA1, &full_bar[stage], (kb - g.kb0) * BK, m_tile * BM);
+              tma_load_2d(sb, &tmB, &full_bar[stage], g.c0 + (kb - g.kb0) * BK, n_tile * BN);
+            }
           } else {
-            tma_load_2d(sa, &tmA1, &full_bar[stage], (kb - g.kb0) * BK, m_tile * BM);
-            tma_load_2d(sb, &tmB, &full_bar[stage], g.c0 + (kb - g.kb0) * BK, n_tile * BN);
+            mbar_expect_tx(&full_bar[stage], g.a_bytes + BN * BK * 2);
+            int kcoord;
+            if (rem < g.kb0) {
+              tma_load_4d(sa, &tmA0, &full_bar[stage], rem * BK, x0 + dx, y0 + dy, n0);
+              kcoord = tap_k + rem * BK;
+            } else {
+              tma_load_4d(sa, &tmA1, &full_bar[stage], (rem - g.kb0) * BK, x0 + dx, y0 + dy, n0);
+              kcoord = tap_k + g.c0 + (rem - g.kb0) * BK;
+            }
+            tma_load_2d(sb, &tmB, &full_bar[stage], kcoord, n_tile * BN);
           }
-        } else {
-          const int tap = kb / kb_per_tap;
-          const int rem = kb - tap * kb_per_tap;
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          mbar_expect_tx(&full_bar[stage], g.a_bytes + BN * BK * 2);
-          int kcoord;
-          if (rem < g.kb0) {
-            tma_load_4d(sa, &tmA0, &full_bar[stage], rem * BK, x0 + dx, y0 + dy, n0);
-            kcoord = tap * g.ctot + rem * BK;
-          } else {
-            tma_load_4d(sa, &tmA1, &full_bar[stage], (rem - g.kb0) * BK, x0 + dx, y0 + dy, n0);
-            kcoord = tap * g.ctot + g.c0 + (rem - g.kb0) * BK;
-          }
-          tma_load_2d(sb, &tmB, &full_bar[stage], kcoord, n_tile * BN);
-        }
         }
         __syncwarp();
+        if (++rem == kb_per_tap) {
+          rem = 0;
+          tap_k += g.ctot;
+          if (++dx == 2) {
+            dx = -1;
+            ++dy;
+          }
+        }
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_f16(BM, BN, kBf16, false, false);
-    uint32_t it = 0, lt = 0;
+    uint32_t lt = 0, stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const uint32_t acc = lt & 1u;
       const uint32_t acc_phase = (lt >> 1) & 1u;
@@ -200,9 +217,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       long long* trm = (ep.trace && blockIdx.x == 0 && lane == 0 && lt < 32) ? ep.trace + 2048 + lt * 16 : nullptr;
       if (trm) trm[0] = clock64();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-        const uint32_t stage = it % Cfg::kStages;
-        const uint32_t phase = (it / Cfg::kStages) & 1u;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (trm && kb < 12) trm[1 + kb] = clock64();
@@ -220,27 +235,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           if (kb == num_k_blocks - 1) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         }
         __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
       if (trm) trm[14] = clock64();
     }
   } else if (warp == 3) {
     // ===================== TMA producer (residual chunks) =====================
     if constexpr (kRes) {
-      // Each epilogue column group owns half of the slots as a private ring (a barrier shared by consumers that can
+      // Each epilogue column group owns a private ring of slots (a barrier shared by consumers that can
       // sit in different phases would let the later one alias a completed phase of the same parity).
-      constexpr int SH = Cfg::kResSlots / 2;
-      constexpr int H0 = (NCHUNK + 1) / 2;
-      uint32_t cnt[2] = {0, 0};
+      constexpr int SH = Cfg::kResPerGroup;
+      constexpr int IMAX = grp_count(NCHUNK, 0);
+      uint32_t cnt[kEpiGroups] = {};
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / num_n_tiles;
         const int n_tile = tile % num_n_tiles;
         int x0, y0, n0;
         tile_origin(m_tile, x0, y0, n0);
-        for (int i = 0; i < H0; ++i) {
+        for (int i = 0; i < IMAX; ++i) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (i >= (h ? NCHUNK - H0 : H0)) continue;
-            const int c = (h ? H0 : 0) + i;
+          for (int h = 0; h < kEpiGroups; ++h) {
+            if (i >= grp_count(NCHUNK, h)) continue;
+            const int c = grp_base(NCHUNK, h) + i;
             const uint32_t k = cnt[h]++;
             const uint32_t slot = h * SH + k % SH;
             mbar_wait(&res_empty[slot], ((k / SH) & 1u) ^ 1u);
@@ -268,10 +287,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int sw = (r >> 1) & 3;  // 64-byte swizzle: 16-byte piece index ^= address bits [7:8]
     uint8_t* obuf_base = sOut + hsel * 2 * kChunk;
     const int bar_id = 2 + hsel;
-    constexpr int H0 = (NCHUNK + 1) / 2;
     const bool do_silu = ep.act == MIMO_ACT_SILU;
     uint32_t lt = 0, oc = 0, rc = 0;
-    long long* tr = (ep.trace && blockIdx.x == 0 && ew == 0 && lane == 0) ? ep.trace + hsel * 1024 : nullptr;
+    long long* tr = (ep.trace && blockIdx.x == 0 && ew == 0 && lane == 0) && hsel < 2 ? ep.trace + hsel * 1024 : nullptr;
     int tk = 0;
 #define GEMM_TR() do { if (tr && lt < 32 && tk < 32) tr[lt * 32 + tk++] = clock64(); } while (0)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
@@ -339,7 +357,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
       float* sb = sbias + acc * 256;
       if (lt == 0 && ce < BN) sb[ce] = load_consts(tile);  // later tiles: staged at the end of the previous tile
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only: constants visible, previous tile retired
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiGroups * 128) : "memory");  // epilogue warps only: constants visible, previous tile retired
       GEMM_TR();  // 1: column constants staged
       // constants of the next tile: the loads fly under this tile's chunks
       const int next_tile = tile + gridDim.x;
@@ -355,8 +373,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       GEMM_TR();  // 2: accumulator ready
 
       if (ep.act != MIMO_ACT_GEGLU) {
-        const int cbase = hsel ? H0 : 0;
-        const int ccount = hsel ? NCHUNK - H0 : H0;
+        const int cbase = grp_base(NCHUNK, hsel);
+        const int ccount = grp_count(NCHUNK, hsel);
         const float scale = ep.scale;
         // one 32-column chunk; the activation is a compile-time tag so the element loop is branch-free
         // kMode 0: no column constants, unit scale, no residual -> accumulators are packed as they are;
@@ -377,7 +395,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           [[maybe_unused]] const uint8_t* rrow = nullptr;
           [[maybe_unused]] uint32_t rslot = 0;
           if constexpr (kRes) {
-            constexpr int SH = Cfg::kResSlots / 2;
+            constexpr int SH = Cfg::kResPerGroup;
             const uint32_t k = rc++;
             rslot = hsel * SH + k % SH;
             mbar_wait(&res_full[rslot], (k / SH) & 1u);
@@ -484,9 +502,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         // between the two warp groups.
         constexpr int HALF = BN / 2;
         constexpr int NPAIR = HALF / 32;
-        constexpr int P0 = (NPAIR + 1) / 2;
-        const int pbase = hsel ? P0 : 0;
-        const int pcount = hsel ? NPAIR - P0 : P0;
+        const int pbase = grp_base(NPAIR, hsel);
+        const int pcount = grp_count(NPAIR, hsel);
 #pragma unroll 1
         for (int i = 0; i < pcount; ++i) {
           {
