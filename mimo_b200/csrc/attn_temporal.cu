@@ -43,6 +43,9 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(smem_u32(p)));
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 template <bool kBf16>
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   if constexpr (kBf16) {
@@ -75,22 +78,36 @@ __global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a) {
   const int dv = d / 8;                              // 16-byte vectors per head row
   const int vec_row = a.hg * dv;
 
-  // ---- stage Q (Fq rows), K, V (F rows) of this pixel; zero what the MMAs read beyond the data ----
-  for (int i = threadIdx.x; i < a.Fq * vec_row; i += blockDim.x) {
-    const int f = i / vec_row, rem = i % vec_row, hh = rem / dv, pc = rem % dv;
-    const long long row = (static_cast<long long>(b) * a.Fq + f) * a.hw + p;
-    *reinterpret_cast<uint4*>(sq + f * pitch + hh * dpad + pc * 8) =
-        *reinterpret_cast<const uint4*>(static_cast<const T*>(a.q) + row * a.ld_q + (hg0 + hh) * d + pc * 8);
-  }
-  for (int i = threadIdx.x; i < a.F * vec_row; i += blockDim.x) {
-    const int f = i / vec_row, rem = i % vec_row, hh = rem / dv, pc = rem % dv;
-    const long long row = static_cast<long long>(f / a.fpc) * a.chunk_stride_rows +
-                          (static_cast<long long>(b) * a.fpc + f % a.fpc) * a.hw + p;
-    const long long off = row * a.ld_kv + (hg0 + hh) * d + pc * 8;
-    *reinterpret_cast<uint4*>(sk + f * pitch + hh * dpad + pc * 8) =
-        *reinterpret_cast<const uint4*>(static_cast<const T*>(a.k) + off);
-    *reinterpret_cast<uint4*>(sv + f * pitch + hh * dpad + pc * 8) =
-        *reinterpret_cast<const uint4*>(static_cast<const T*>(a.v) + off);
+  // ---- stage Q (Fq rows), K, V (F rows) of this pixel with 16-byte cp.async ----
+  // A warp takes whole frames; a lane's vectors inside the row segment do not depend on the frame, so their
+  // (head, piece) split - the only divisions - is done once. (The first version recomputed three divisions and a
+  // 64-bit row product per 16-byte vector: ~18k warp instructions per CTA, issue-bound at 2 TB/s.)
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    int soff[4], goff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int v = lane + 32 * j;
+      const int hh = v / dv, pc = v - hh * dv;
+      soff[j] = v < vec_row ? hh * dpad + pc * 8 : -1;
+      goff[j] = (hg0 + hh) * d + pc * 8;
+    }
+    for (int f = warp; f < a.F; f += nwarps) {
+      const long long kvrow = static_cast<long long>(f / a.fpc) * a.chunk_stride_rows +
+                              (static_cast<long long>(b) * a.fpc + f % a.fpc) * a.hw + p;
+      const T* kr = static_cast<const T*>(a.k) + kvrow * a.ld_kv;
+      const T* vr = static_cast<const T*>(a.v) + kvrow * a.ld_kv;
+      const T* qr = static_cast<const T*>(a.q) + ((static_cast<long long>(b) * a.Fq + f) * a.hw + p) * a.ld_q;
+      const bool has_q = f < a.Fq;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (soff[j] >= 0) {
+          cp_async16(sk + f * pitch + soff[j], kr + goff[j]);
+          cp_async16(sv + f * pitch + soff[j], vr + goff[j]);
+          if (has_q) cp_async16(sq + f * pitch + soff[j], qr + goff[j]);
+        }
+      }
+    }
   }
   if (dpad > d) {  // zero the K-dimension padding of Q and K (d = 40 -> 48)
     const int padv = (dpad - d) / 8;
@@ -105,6 +122,7 @@ __global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a) {
     const int f = a.F + i / (pitch / 8), pc = i % (pitch / 8);
     *reinterpret_cast<uint4*>(sv + f * pitch + pc * 8) = make_uint4(0, 0, 0, 0);
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   const int hh = threadIdx.x >> 5;  // head within the group
@@ -208,11 +226,15 @@ __global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a) {
     }
   }
   __syncwarp();
-  for (int i = lane; i < a.Fq * dv; i += 32) {
-    const int f = i / dv, pc = i % dv;
-    const long long row = (static_cast<long long>(b) * a.Fq + f) * a.hw + p;
-    *reinterpret_cast<uint4*>(static_cast<T*>(a.out) + row * a.ld_out + (hg0 + hh) * d + pc * 8) =
-        *reinterpret_cast<const uint4*>(oh + f * pitch + pc * 8);
+  {
+    const int lf = lane / dv, lpc = lane - lf * dv, fstep = 32 / dv;  // 32 / dv frames per pass, one vector per lane
+    if (lf < fstep) {
+      for (int f = lf; f < a.Fq; f += fstep) {
+        const long long row = (static_cast<long long>(b) * a.Fq + f) * a.hw + p;
+        *reinterpret_cast<uint4*>(static_cast<T*>(a.out) + row * a.ld_out + (hg0 + hh) * d + lpc * 8) =
+            *reinterpret_cast<const uint4*>(oh + f * pitch + lpc * 8);
+      }
+    }
   }
 }
 
@@ -224,7 +246,7 @@ extern "C" int mimo_attn_temporal(const mimo_attn_temporal_params* p, void* stre
   if (!p || !p->q || !p->k || !p->v || !p->out) return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: null pointer");
   const int fpc = p->frames_per_chunk > 0 ? p->frames_per_chunk : p->kv_frames;
   if (p->batch <= 0 || p->q_frames <= 0 || p->kv_frames <= 0 || p->kv_frames > 32 || p->q_frames > 32 || p->hw <= 0 ||
-      p->heads <= 0 || p->heads > 32 || p->d <= 0 || (p->d % 8) || (p->ld_q % 8) || (p->ld_kv % 8) || (p->ld_out % 8) ||
+      p->heads <= 0 || p->heads > 32 || p->d <= 0 || (p->d % 8) || p->d > 256 || (p->ld_q % 8) || (p->ld_kv % 8) || (p->ld_out % 8) ||
       (p->kv_frames % fpc))
     return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: need frames <= 32, heads <= 32, d % 8 == 0, kv_frames % chunk == 0");
   if (int rc = ensure_device()) return rc;
