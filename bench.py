@@ -156,6 +156,13 @@ def run_ours(args):
     # ---- device-resident runs (value) ------------------------------------------------------------------
     host = pipe.preprocess(ref_img, poses, bks, WIDTH, HEIGHT, FRAMES, clip_seed(0), torch.float16)
     dev_in = {k: v.to(device) for k, v in host.items()}
+    if args.one_clip:
+        t0 = time.perf_counter()
+        pipe.sample_tensors(dev_in, DDIM_STEPS, GUIDANCE)
+        sync()
+        if rank == 0:
+            print(json.dumps({"one_clip_s": round(time.perf_counter() - t0, 3), "note": "profiling aid, not a bench value"}))
+        return
     for i in range(args.warmup):
         pipe.sample_tensors(dev_in, DDIM_STEPS, GUIDANCE)
     sync()
@@ -334,6 +341,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dump-calls", default=None, help="write every profiled C-ABI call (name, flops, bytes, ms) as CSV")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU sample (development runs)")
+    ap.add_argument("--one-clip", action="store_true",
+                    help="run exactly one device-resident clip and exit (for `ncu` launch lists; not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps, args.warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
