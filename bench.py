@@ -238,14 +238,28 @@ def run_ours(args):
     for name, (t_ms, fl, by, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         breakdown[name] = {"ms": round(t_ms, 2), "share": round(t_ms / total_ms, 4), "launches": cnt,
                            "tflops": round(fl / t_ms / 1e9, 1) if fl else None, "gbs": round(by / t_ms / 1e6, 1)}
-    dom = max(agg.items(), key=lambda kv: kv[1][0])
-    dname, (dms, dfl, dby, dcnt) = dom
-    tensor_bound = dname in ("gemm", "conv3x3", "attn_spatial")
+    # The dominant kernel is gemm_tcgen05_kernel: the plain GEMMs ("gemm") and the implicit-GEMM 3x3 convolutions
+    # ("conv3x3") are the same kernel template in its two addressing modes.
+    fam = {"gemm_tcgen05_kernel": ("gemm", "conv3x3"), "attn_spatial": ("attn_spatial",)}
+    fam_ms = {k: sum(agg[n][0] for n in names if n in agg) for k, names in fam.items()}
+    others = {n: agg[n][0] for n in agg if not any(n in names for names in fam.values())}
+    dname = max({**fam_ms, **others}.items(), key=lambda kv: kv[1])[0]
+    members = fam.get(dname, (dname,))
+    dms = sum(agg[n][0] for n in members if n in agg)
+    dfl = sum(agg[n][1] for n in members if n in agg)
+    dby = sum(agg[n][2] for n in members if n in agg)
+    dcnt = sum(agg[n][3] for n in members if n in agg)
+    tensor_bound = dname in ("gemm_tcgen05_kernel", "attn_spatial")
     achieved = dfl / dms / 1e9 if tensor_bound else dby / dms / 1e6
     peak = peak_tf if tensor_bound else peak_gbs
+    traffic = None  # DRAM bytes per launch of this kernel from the committed ncu capture (profiles/)
+    tpath = Path(__file__).resolve().parent / "profiles" / "ncu_traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text()).get(dname, {}).get("dram_bytes_per_launch")
     roofline = {"kernel": dname, "bound": "tensor" if tensor_bound else "hbm", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src, "launches": dcnt, "avg_launch_ms": round(dms / dcnt, 4),
+                "traffic": traffic, "algorithmic_bytes_per_launch": round(dby / dcnt), "peak_source": peak_src,
+                "launches": dcnt, "avg_launch_ms": round(dms / dcnt, 4), "share_of_step": round(dms / total_ms, 4),
                 "whole_path_frac_of_tensor_peak": round(TFLOP_PER_FRAME * value / (world * peak_tf), 4)}
 
     if rank != 0:
