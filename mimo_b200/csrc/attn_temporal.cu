@@ -61,8 +61,17 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
   }
 }
 
-template <bool kBf16>
-__global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a) {
+// D / HG > 0: head dim and heads per CTA fixed at compile time (the UNet's three levels: 40x8, 80x4, 160x2), which
+// turns the row pitch and every fragment address into immediates; D = 0: generic (runtime) geometry.
+template <bool kBf16, int D, int HG>
+__global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a_in) {
+  TemporalArgs a = a_in;
+  if constexpr (D > 0) {
+    a.d = D;
+    a.dpad = (D + 15) / 16 * 16;
+    a.hg = HG;
+    a.pitch = HG * ((D + 15) / 16 * 16) + 8;
+  }
   using C = Cvt<kBf16>;
   using T = typename C::T;
   extern __shared__ uint4 smem_qkv[];
@@ -109,18 +118,20 @@ __global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a) {
       }
     }
   }
-  if (dpad > d) {  // zero the K-dimension padding of Q and K (d = 40 -> 48)
-    const int padv = (dpad - d) / 8;
-    for (int i = threadIdx.x; i < 32 * a.hg * padv; i += blockDim.x) {
-      const int f = i / (a.hg * padv), rem = i % (a.hg * padv), hh = rem / padv, pc = rem % padv;
-      *reinterpret_cast<uint4*>(sq + f * pitch + hh * dpad + d + pc * 8) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sk + f * pitch + hh * dpad + d + pc * 8) = make_uint4(0, 0, 0, 0);
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (dpad > d) {  // zero the K-dimension padding of Q and K (d = 40 -> 48): lane = head, warp strides the rows
+      const int padv = (dpad - d) / 8;
+      for (int f = warp; f < 32; f += nwarps)
+        for (int hh = lane; hh < a.hg; hh += 32)
+          for (int pc = 0; pc < padv; ++pc) {
+            *reinterpret_cast<uint4*>(sq + f * pitch + hh * dpad + d + pc * 8) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(sk + f * pitch + hh * dpad + d + pc * 8) = make_uint4(0, 0, 0, 0);
+          }
     }
-  }
-  // V rows beyond F multiply probabilities that are exactly 0: they must be finite -> zero them
-  for (int i = threadIdx.x; i < (32 - a.F) * (pitch / 8); i += blockDim.x) {
-    const int f = a.F + i / (pitch / 8), pc = i % (pitch / 8);
-    *reinterpret_cast<uint4*>(sv + f * pitch + pc * 8) = make_uint4(0, 0, 0, 0);
+    // V rows beyond F multiply probabilities that are exactly 0: they must be finite -> zero them
+    for (int f = a.F + warp; f < 32; f += nwarps)
+      for (int pc = lane; pc < pitch / 8; pc += 32) *reinterpret_cast<uint4*>(sv + f * pitch + pc * 8) = make_uint4(0, 0, 0, 0);
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -131,6 +142,7 @@ __global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a) {
   const int g = lane >> 2, t = lane & 3;
   const int MT = (a.Fq + 15) >> 4;  // 16-row query tiles
   const int NT = (a.F + 7) >> 3;    // 8-key tiles
+  const bool ragged = (a.F & 7) != 0;
   const T* qh = sq + hh * dpad;
   const T* kh = sk + hh * dpad;
   const T* vh = sv + hh * dpad;
@@ -173,25 +185,31 @@ __global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a) {
     for (int half = 0; half < 2; ++half) {  // half 0: row g, half 1: row g + 8
       float m = -INFINITY;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt < NT) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = nt * 8 + 2 * t + e;
-          float& v = s[mt][nt][half * 2 + e];
-          v = (col < a.F) ? v * a.scale_log2 : -INFINITY;
-          m = fmaxf(m, v);
+          for (int e = 0; e < 2; ++e) {
+            float& v = s[mt][nt][half * 2 + e];
+            v *= a.scale_log2;
+            if (ragged && nt == NT - 1 && nt * 8 + 2 * t + e >= a.F) v = -INFINITY;
+            m = fmaxf(m, v);
+          }
         }
+      }
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
       float sum = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt < NT) {  // key tiles beyond NT keep their zero accumulators: P = 0 there
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          float& v = s[mt][nt][half * 2 + e];
-          v = exp2f(v - m);  // exp2f(-inf) = 0 for the masked keys
-          sum += v;
+          for (int e = 0; e < 2; ++e) {
+            float& v = s[mt][nt][half * 2 + e];
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(v - m));  // ex2(-inf) = 0 for the masked keys
+            sum += v;
+          }
         }
+      }
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
       inv_sum[mt][half] = 1.0f / sum;
@@ -280,23 +298,27 @@ extern "C" int mimo_attn_temporal(const mimo_attn_temporal_params* p, void* stre
   const long long nblk = static_cast<long long>(p->batch) * p->hw * (p->heads / hg);
   if (nblk > 0x7fffffffLL) return set_error(MIMO_ERR_ARG, "mimo_attn_temporal: grid too large");
   const unsigned grid = static_cast<unsigned>(nblk);
-  static bool attr_done[2] = {false, false};
   cudaError_t e;
-  if (p->dtype == MIMO_BF16) {
-    if (!attr_done[1]) {
-      e = cudaFuncSetAttribute(attn_temporal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return set_cuda_error("attn_temporal attr", e);
-      attr_done[1] = true;
+  static bool attr_done[8] = {};  // per kernel instantiation
+  auto launch = [&](void (*kern)(TemporalArgs), int id) -> cudaError_t {
+    if (!attr_done[id]) {
+      cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (ea != cudaSuccess) return ea;
+      attr_done[id] = true;
     }
-    attn_temporal_kernel<true><<<grid, threads, smem, st>>>(a);
-  } else {
-    if (!attr_done[0]) {
-      e = cudaFuncSetAttribute(attn_temporal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return set_cuda_error("attn_temporal attr", e);
-      attr_done[0] = true;
-    }
-    attn_temporal_kernel<false><<<grid, threads, smem, st>>>(a);
-  }
+    kern<<<grid, threads, smem, st>>>(a);
+    return cudaSuccess;
+  };
+  const bool bf = p->dtype == MIMO_BF16;
+  if (a.d == 40 && hg == 8)
+    e = bf ? launch(attn_temporal_kernel<true, 40, 8>, 0) : launch(attn_temporal_kernel<false, 40, 8>, 1);
+  else if (a.d == 80 && hg == 4)
+    e = bf ? launch(attn_temporal_kernel<true, 80, 4>, 2) : launch(attn_temporal_kernel<false, 80, 4>, 3);
+  else if (a.d == 160 && hg == 2)
+    e = bf ? launch(attn_temporal_kernel<true, 160, 2>, 4) : launch(attn_temporal_kernel<false, 160, 2>, 5);
+  else
+    e = bf ? launch(attn_temporal_kernel<true, 0, 0>, 6) : launch(attn_temporal_kernel<false, 0, 0>, 7);
+  if (e != cudaSuccess) return set_cuda_error("attn_temporal attr", e);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("attn_temporal launch", e);
   return MIMO_OK;
