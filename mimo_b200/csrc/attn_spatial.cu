@@ -54,12 +54,12 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_done = p_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x;
   const int h = blockIdx.y;
   const int n = blockIdx.z;
-  const int bidx = a.bank_index ? a.bank_index[n] : -1;
+  const int bidx = __shfl_sync(0xffffffffu, a.bank_index ? a.bank_index[n] : -1, 0);
   const int T = a.n_self_tiles + (bidx >= 0 ? a.n_bank_tiles : 0);
 
   if (warp == 0 && lane == 0) {
@@ -86,7 +86,7 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tmem_S = tmem_base;        // 128 fp32 columns
   const uint32_t tmem_O = tmem_base + 128;  // dp fp32 columns
 
@@ -113,8 +113,8 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma_load_4d(sv + ch * kChunkBytes, mv, &kv_full[stage], ch * 64, h, row0, img);
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues: descriptors stay uniform) =====================
     const uint32_t idesc_qk = make_idesc_f16(BQ, BKV, kBf16, false, false);
     const uint32_t idesc_pv = make_idesc_f16(BQ, a.dp, kBf16, false, true);  // B (= V) is MN-major
     const int ksteps_qk = a.dp / 16;
@@ -123,12 +123,15 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto issue_qk = [&](int j) {
       const int stage = j % KVST;
       const uint32_t k_addr = smem_u32(sKV + stage * Cfg::kKVStageBytes);
-      for (int ks = 0; ks < ksteps_qk; ++ks) {
-        const uint32_t off = (ks >> 2) * kChunkBytes + (ks & 3) * 32;
-        umma_ss(tmem_S, make_smem_desc_sw128(q_addr + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024),
-                idesc_qk, ks != 0 ? 1u : 0u);
+      if (elect_one()) {
+        for (int ks = 0; ks < ksteps_qk; ++ks) {
+          const uint32_t off = (ks >> 2) * kChunkBytes + (ks & 3) * 32;
+          umma_ss(tmem_S, make_smem_desc_sw128(q_addr + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024),
+                  idesc_qk, ks != 0 ? 1u : 0u);
+        }
+        tc_commit(s_full);
       }
-      tc_commit(s_full);
+      __syncwarp();
     };
     mbar_wait(q_full, 0);
     mbar_wait(&kv_full[0], 0);
@@ -139,16 +142,19 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(p_full, j & 1);
       tc_fence_after();
       const uint32_t v_addr = smem_u32(sKV + stage * Cfg::kKVStageBytes + NCH * kChunkBytes);
+      if (elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < BKV / 16; ++ks) {
-        // A = P: K-major, 64-key chunks of [128 rows x 128 B]; B = V: MN-major, 16 keys = 2 KiB further down
-        const uint32_t pa = p_addr + (ks >> 2) * kChunkBytes + (ks & 3) * 32;
-        const uint32_t vb = v_addr + ks * 2048;
-        umma_ss(tmem_O, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(vb, kChunkBytes, 1024), idesc_pv,
-                (j | ks) != 0 ? 1u : 0u);
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          // A = P: K-major, 64-key chunks of [128 rows x 128 B]; B = V: MN-major, 16 keys = 2 KiB further down
+          const uint32_t pa = p_addr + (ks >> 2) * kChunkBytes + (ks & 3) * 32;
+          const uint32_t vb = v_addr + ks * 2048;
+          umma_ss(tmem_O, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(vb, kChunkBytes, 1024), idesc_pv,
+                  (j | ks) != 0 ? 1u : 0u);
+        }
+        tc_commit(&kv_empty[stage]);
+        tc_commit(o_done);
       }
-      tc_commit(&kv_empty[stage]);
-      tc_commit(o_done);
+      __syncwarp();
       if (j + 1 < T) {
         const int ns = (j + 1) % KVST;
         mbar_wait(&kv_full[ns], ((j + 1) / KVST) & 1u);
