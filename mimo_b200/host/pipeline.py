@@ -29,15 +29,42 @@ class Pose2VideoPipelineOutput:
     videos: Union[torch.Tensor, np.ndarray]
 
 
-def pil_to_tensor(images, height: int, width: int, normalize: bool, scale_factor: int = 8) -> torch.Tensor:
-    """diffusers VaeImageProcessor(do_convert_rgb=True).preprocess [3P] as used at pipeline :73-80, :424-426, :436,
-    :448-450: RGB -> LANCZOS resize to (w, h) floored to multiples of 8 -> [0, 1] -> NCHW -> 2x - 1 if normalize."""
+def pil_to_uint8(images, height: int, width: int, scale_factor: int = 8) -> torch.Tensor:
+    """First half of diffusers VaeImageProcessor(do_convert_rgb=True).preprocess [3P] (pipeline :73-80, :424-426,
+    :436, :448-450): RGB -> LANCZOS resize to (w, h) floored to multiples of 8, kept as uint8 [N, H, W, 3]."""
     imgs = images if isinstance(images, (list, tuple)) else [images]
     w, h = width - width % scale_factor, height - height % scale_factor
-    arr = np.stack([np.asarray(i.convert("RGB").resize((w, h), resample=PIL.Image.LANCZOS), dtype=np.float32) / 255.0
-                    for i in imgs])
-    t = torch.from_numpy(arr).permute(0, 3, 1, 2).contiguous()
+    return torch.from_numpy(np.stack([np.asarray(i.convert("RGB").resize((w, h), resample=PIL.Image.LANCZOS), dtype=np.uint8)
+                                      for i in imgs]))
+
+
+def uint8_to_tensor(u8: torch.Tensor, normalize: bool) -> torch.Tensor:
+    """Second half, on whatever device `u8` lives on: [N, H, W, 3] uint8 -> fp32 NCHW in [0, 1], then 2x - 1 if
+    `normalize`. The same IEEE fp32 division / multiply / subtract as the host version: results are bit-identical,
+    the clip's images just cross PCIe as bytes and the 38 M-element conversion runs on the GPU instead of one core."""
+    t = u8.permute(0, 3, 1, 2).to(torch.float32) / 255.0
     return 2.0 * t - 1.0 if normalize else t
+
+
+def pil_to_tensor(images, height: int, width: int, normalize: bool, scale_factor: int = 8) -> torch.Tensor:
+    """The full VaeImageProcessor.preprocess on the host (used by the tests and the oracle)."""
+    return uint8_to_tensor(pil_to_uint8(images, height, width, scale_factor), normalize).contiguous()
+
+
+def _dedupe_images(images) -> "tuple[list, torch.Tensor]":
+    """Indices of the first occurrence of every distinct image (by size, mode and pixel bytes) and, per image, the
+    index of its representative among those: animate mode passes one identical white background per frame
+    (run_animate.py:174-177) and the VAE should see it once."""
+    import zlib
+    first, inverse, seen = [], [], {}
+    for i, im in enumerate(images):
+        raw = im.tobytes()
+        key = (im.size, im.mode, len(raw), zlib.crc32(raw), zlib.adler32(raw))
+        if key not in seen:
+            seen[key] = len(first)
+            first.append(i)
+        inverse.append(seen[key])
+    return first, torch.tensor(inverse, dtype=torch.long)
 
 
 class Pose2VideoPipeline:
@@ -126,17 +153,14 @@ class Pose2VideoPipeline:
         """Host side of __call__: PIL -> pinned CPU tensors (what the reference does at pipeline :379-381, :409-418,
         :424-426, :435-437, :446-453 before anything touches the device)."""
         pin = lambda t: t.contiguous().pin_memory() if torch.cuda.is_available() else t.contiguous()
-        bk = pil_to_tensor(list(vid_bk_images), height, width, normalize=True)
-        # identical background frames (animate mode: every frame white, run_animate.py:174-177) are encoded once
-        uniq, inverse = torch.unique(bk.flatten(1), dim=0, return_inverse=True)
-        first = torch.stack([(inverse == i).nonzero()[0, 0] for i in range(uniq.shape[0])])
-        pose = pil_to_tensor(list(pose_images), height, width, normalize=False)  # [F, 3, H, W] in [0, 1]
+        bks = list(vid_bk_images)
+        first, inverse = _dedupe_images(bks)  # identical background frames are converted, copied and encoded once
         return {
             "clip_pixels": pin(self._clip_pixels(ref_image)),
-            "ref": pin(pil_to_tensor(ref_image, height, width, normalize=True).to(dtype)),
-            "bk_unique": pin(bk[first].to(dtype)),
+            "ref_u8": pin(pil_to_uint8(ref_image, height, width)),
+            "bk_unique_u8": pin(pil_to_uint8([bks[i] for i in first], height, width)),
             "bk_inverse": inverse,
-            "pose": pin(pose.permute(1, 0, 2, 3).unsqueeze(0).to(dtype)),
+            "pose_u8": pin(pil_to_uint8(list(pose_images), height, width)),  # [F, H, W, 3]
             "latents": pin(self.prepare_latents(1, 4, width, height, video_length, dtype, "cpu", generator)),
         }
 
@@ -170,8 +194,12 @@ class Pose2VideoPipeline:
         latents = inp["latents"].to(dtype).clone()
         F_, h, w = latents.shape[2], latents.shape[3], latents.shape[4]
         enc, _ = self._vae()
-        ref_latents = enc.encode_mean(inp["ref"]) * 0.18215  # :424-431
-        bk_lat = (enc.encode_mean(inp["bk_unique"]) * 0.18215)[inp["bk_inverse"].to(device)]
+        # bytes -> normalised pixels on the device (pipeline :424-426, :435-437, :446-453)
+        ref_px = uint8_to_tensor(inp["ref_u8"], True).to(dtype)
+        bk_px = uint8_to_tensor(inp["bk_unique_u8"], True).to(dtype)
+        pose_px = uint8_to_tensor(inp["pose_u8"], False).permute(1, 0, 2, 3).unsqueeze(0).to(dtype)  # [1, 3, F, H, W]
+        ref_latents = enc.encode_mean(ref_px) * 0.18215  # :424-431
+        bk_lat = (enc.encode_mean(bk_px) * 0.18215)[inp["bk_inverse"].to(device)]
         vid_bk = bk_lat.permute(1, 0, 2, 3).unsqueeze(0).to(dtype).contiguous()  # [1, 4, F, h, w]  :434-443
         mark("vae_encode")
 
@@ -180,14 +208,14 @@ class Pose2VideoPipeline:
             import torch.distributed as dist
             if F_ % world == 0:  # pose features: each rank computes its frames, then all-gather [F, hw, 320]
                 fl = F_ // world
-                loc = self.pose_guider.forward_nhwc(inp["pose"][:, :, rank * fl:(rank + 1) * fl].contiguous())
+                loc = self.pose_guider.forward_nhwc(pose_px[:, :, rank * fl:(rank + 1) * fl].contiguous())
                 pose_all = torch.empty((world * loc.shape[0], loc.shape[1]), dtype=loc.dtype, device=device)
                 dist.all_gather_into_tensor(pose_all, loc.contiguous(), group=group)
                 pose_fea = pose_all.reshape(F_, h * w, -1)
             else:
-                pose_fea = self.pose_guider.forward_nhwc(inp["pose"]).reshape(F_, h * w, -1)
+                pose_fea = self.pose_guider.forward_nhwc(pose_px).reshape(F_, h * w, -1)
         else:
-            pose_fea = self.pose_guider.forward_nhwc(inp["pose"]).reshape(F_, h * w, -1)  # channels-last, per frame
+            pose_fea = self.pose_guider.forward_nhwc(pose_px).reshape(F_, h * w, -1)  # channels-last, per frame
         mark("pose_guider")
 
         # reference UNet once, banks -> denoising engine (pipeline :393-406, :480-490)
@@ -285,8 +313,12 @@ class Pose2VideoPipeline:
         self.io_bytes["h2d"] = sum(v.numel() * v.element_size() for v in host.values())
         out = self.sample_tensors(dev_in, num_inference_steps, guidance_scale, context_schedule, context_frames,
                                   context_stride, context_overlap, callback, callback_steps)
-        images = out["videos"].cpu().float().numpy()  # :124-126: one D2H of the finished clip
-        self.io_bytes["d2h"] = out["videos"].numel() * out["videos"].element_size()
+        vid = out["videos"]
+        host_vid = torch.empty(vid.shape, dtype=vid.dtype, pin_memory=True)
+        host_vid.copy_(vid, non_blocking=True)  # :124-126: one D2H of the finished clip, into pinned memory
+        torch.cuda.synchronize(device)
+        images = host_vid.float().numpy()
+        self.io_bytes["d2h"] = vid.numel() * vid.element_size()
         self._collect_timings()
         if output_type == "tensor":
             images = torch.from_numpy(images)

@@ -85,3 +85,37 @@ def test_unsupported_configurations_fail_loudly():
     assert m.state_dict()["conv_in.weight"].shape[1] == 8  # forced 8 input channels
     with pytest.raises(NotImplementedError):
         ReferenceAttentionControl(m, mode="read", fusion_blocks="midup")
+
+
+def test_image_preprocessing_is_the_vae_image_processor_bit_for_bit():
+    """pipeline :73-80 / :424-453: the byte-level host path + device-side normalisation must reproduce
+    VaeImageProcessor.preprocess (RGB, LANCZOS to multiples of 8, /255, NCHW, optional 2x-1) exactly."""
+    import numpy as np
+    import PIL.Image
+
+    from mimo_b200.host import pipeline as P
+    rng = np.random.RandomState(3)
+    imgs = [PIL.Image.fromarray(rng.randint(0, 256, (70, 90, 3), dtype=np.uint8)) for _ in range(3)]
+    imgs.append(PIL.Image.fromarray(rng.randint(0, 256, (64, 64), dtype=np.uint8)))  # grayscale -> RGB
+    for size in (64, 61):  # 61 -> floored to 56
+        w = h = size - size % 8
+        arr = np.stack([np.asarray(i.convert("RGB").resize((w, h), resample=PIL.Image.LANCZOS), dtype=np.float32) / 255.0
+                        for i in imgs])
+        want = torch.from_numpy(arr).permute(0, 3, 1, 2).contiguous()
+        assert torch.equal(P.pil_to_tensor(imgs, size, size, False), want)
+        assert torch.equal(P.pil_to_tensor(imgs, size, size, True), 2.0 * want - 1.0)
+        u8 = P.pil_to_uint8(imgs, size, size)
+        assert u8.dtype == torch.uint8 and tuple(u8.shape) == (len(imgs), h, w, 3)
+
+
+def test_identical_background_frames_are_deduplicated():
+    import numpy as np
+    import PIL.Image
+
+    from mimo_b200.host import pipeline as P
+    white = lambda: PIL.Image.fromarray(np.full((32, 32, 3), 255, np.uint8))
+    other = PIL.Image.fromarray(np.zeros((32, 32, 3), np.uint8))
+    first, inverse = P._dedupe_images([white(), white(), other, white(), other])
+    assert first == [0, 2] and inverse.tolist() == [0, 0, 1, 0, 1]
+    first, inverse = P._dedupe_images([other])
+    assert first == [0] and inverse.tolist() == [0]
