@@ -1,12 +1,14 @@
 // Spatial self-attention with the reference bank, head dim <= 64 (the UNet's 64x64 level: d = 40, 87 % of all
 // attention FLOPs): flash attention with TWO 128-row query tiles per CTA processed in ping-pong.
 //
-//   warp 0 lane 0 : TMA      - Q tiles A and B once; K/V tiles in a 2-stage ring shared by both query tiles
-//   warp 1 lane 0 : MMA      - S_X = Q_X K^T (128x128xdp) and O_X += P_X V (128xdpx128), X in {A, B}, interleaved so
-//                              the tensor pipe works on one query tile while the other one is in its softmax
+//   warp 0 lane 0 : TMA      - Q tiles A and B once; K/V tiles in rings shared by both query tiles
+//   warp 1 / 3    : MMA      - warp 1 drives query tile A, warp 3 tile B (whole warp + one elected lane, descriptors in
+//                              uniform registers): S_X = Q_X K^T (128x128xdp) as soon as the softmax group has pulled
+//                              the previous S_X into registers, O_X += P_X V (128xdpx128) when P_X is in shared memory
 //   warp 2        : TMEM allocator (512 columns: S_A, S_B, O_A, O_B)
 //   warps 4-7     : softmax warpgroup A (one thread per query row = TMEM lane)
-//   warps 8-11    : softmax warpgroup B
+//   warps 8-11    : softmax warpgroup B - started one exponential phase after A, so that one group's loads, stores and
+//                              waits run under the other group's MUFU work instead of both idling the pipe together
 // A softmax thread pulls its whole 128-key row of S into registers (128 of the 168 the launch bound allows) and
 // releases S_X at once, so Q_X K[j+1]^T runs underneath the exponentials of tile j and
 // the MUFU pipe - the bound of this kernel at d = 40 - never waits for the tensor pipe.

@@ -4,16 +4,19 @@
 //
 // One CTA per SM loops over 128 x BN output tiles (static round-robin schedule, n-tile fastest so that CTAs
 // running concurrently share A tiles in L2). Every byte that crosses the SM boundary moves by TMA; no thread issues
-// a scattered global load or store on the steady-state path. Roles (384 threads):
-//   warp 0 lane 0 : TMA producer   - ring of {A 128x64, W BNx64} 128B-swizzled stages
-//   warp 1 lane 0 : MMA issuer     - tcgen05.mma.cta_group::1.kind::f16 128xBNx16; accumulators double-buffered in
+// a scattered global load or store on the steady-state path. Roles (512 threads; the producer / issuer warps run
+// their loops with all 32 lanes and elect one lane per TMA / tcgen05 instruction, which keeps addresses and
+// descriptors in uniform registers):
+//   warp 0        : TMA producer   - ring of {A 128x64, W BNx64} 128B-swizzled stages
+//   warp 1        : MMA issuer     - tcgen05.mma.cta_group::1.kind::f16 128xBNx16; accumulators double-buffered in
 //                                    TMEM so the epilogue of tile i overlaps the main loop of tile i+1
 //   warp 2        : TMEM allocator
-//   warp 3 lane 0 : residual producer (kRes) - TMA boxes of the residual tensor, 128 rows x 32 columns each, into a
-//                                    ring of 8 KiB slots that runs ahead of the epilogue
-//   warps 4..11   : epilogue       - two groups of 4 warps split the tile's 32-column chunks. Per chunk: tcgen05.ld
-//                                    32 lanes x 32 columns -> + bias / per-branch vector (smem) + residual (smem ring)
-//                                    -> scale / SiLU / GEGLU -> 64B-swizzled staging buffer -> TMA store
+//   warp 3        : residual producer (kRes) - TMA boxes of the residual tensor, 128 rows x 32 columns each, into a
+//                                    private ring of 8 KiB slots per epilogue group
+//   warps 4..15   : epilogue       - three groups of 4 warps deal out the tile's 32-column chunks. Per chunk:
+//                                    tcgen05.ld 32 lanes x 32 columns -> acc * scale + column constants (bias +
+//                                    per-branch vector, staged in smem one tile ahead) + residual (smem ring)
+//                                    -> SiLU / GEGLU -> 64B-swizzled staging buffer -> TMA store
 // Convolution mode replaces the A loads by 4-D TMA boxes {64 ch, TW, TH, TN} over the NHWC input, one box per
 // (tap, 64-channel block, source tensor); TMA's out-of-bounds zero fill is the conv's zero padding and also
 // the K tail, and the output / residual boxes use the same {TW, TH, TN} footprint (stores are clipped at image
@@ -499,7 +502,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
       } else {
         // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates; 32-column pairs are split
-        // between the two warp groups.
+        // dealt out to the epilogue groups.
         constexpr int HALF = BN / 2;
         constexpr int NPAIR = HALF / 32;
         const int pbase = grp_base(NPAIR, hsel);
