@@ -283,6 +283,9 @@ def run_ours(args):
 # =====================================================================================================
 # CPU baseline: the oracle port of the reference's PyTorch graph on the host cores
 # =====================================================================================================
+_CPU_WEIGHTS: dict = {}
+
+
 def usable_cores() -> int:
     """Host threads this process may really use: CPU affinity, capped by a cgroup CPU quota if there is one
     (`os.cpu_count()` reports the machine, not the container)."""
@@ -333,8 +336,10 @@ def cpu_baseline_sample(seed: int = 0) -> dict:
     cores = pick_cpu_threads()
     torch.set_num_threads(cores)
     cfg, vcfg = O.UNetConfig(), O.VAEConfig()
-    sd_den, sd_ref = O.make_denoising_unet_sd(cfg, 1), O.make_reference_unet_sd(cfg, 2)
-    sd_vae = O.make_vae_sd(vcfg, 4)
+    if not _CPU_WEIGHTS:  # seeded random weights, built once per process (20 s of the first sample otherwise)
+        _CPU_WEIGHTS.update(den=O.make_denoising_unet_sd(cfg, 1), ref=O.make_reference_unet_sd(cfg, 2),
+                            vae=O.make_vae_sd(vcfg, 4))
+    sd_den, sd_ref, sd_vae = _CPU_WEIGHTS["den"], _CPU_WEIGHTS["ref"], _CPU_WEIGHTS["vae"]
     g = torch.Generator().manual_seed(seed)
     # bounded sample: 1 of the 24 frames at a quarter of the pixels (32x32 latents = 256x256 px). Scaling the times by
     # x4 pixels x24 frames is LINEAR, i.e. it ignores that spatial attention grows quadratically with the pixel count:
