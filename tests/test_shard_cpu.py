@@ -51,3 +51,13 @@ def test_frame_sharding_layout_gloo_world2():
     port = 29500 + os.getpid() % 400
     mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
     assert all(results[r] for r in range(world))
+
+
+def test_frame_sharding_layout_gloo_world4():
+    """Same invariants with four ranks (6 frames of a 24-frame window each): the scaling runs go up to 8 GPUs."""
+    world = 4
+    mgr = mp.Manager()
+    results = mgr.dict()
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+    assert all(results[r] for r in range(world))
