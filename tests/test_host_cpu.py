@@ -119,3 +119,29 @@ def test_identical_background_frames_are_deduplicated():
     assert first == [0, 2] and inverse.tolist() == [0, 0, 1, 0, 1]
     first, inverse = P._dedupe_images([other])
     assert first == [0] and inverse.tolist() == [0]
+
+
+def test_weight_packers_lay_out_what_the_kernels_index():
+    """Host-side packing only (no device): conv weights become [cout, 9 * cin] with K = (ky*3+kx) * cin + ch (the order
+    the implicit-GEMM producer walks taps and channel blocks in), GEGLU projections interleave value / gate rows per
+    output tile so that one accumulator tile holds both halves of the same columns."""
+    from mimo_b200 import lib as L
+    from mimo_b200 import ops
+    w = torch.arange(5 * 3 * 3 * 3, dtype=torch.float32).reshape(5, 3, 3, 3)
+    p = ops.pack_conv3x3_weight(w)
+    assert tuple(p.shape) == (8, 9 * 8)
+    for co, ky, kx, ch in [(0, 0, 0, 0), (4, 2, 1, 2), (3, 1, 2, 1)]:
+        assert p[co, (ky * 3 + kx) * 8 + ch] == w[co, ch, ky, kx]
+    assert float(p[5:].abs().sum()) == 0.0 and float(p[:, 3:8].abs().sum()) == 0.0  # channel / row padding is zero
+
+    n2, dim = 2560, 16
+    g = L.load().mimo_gemm_geglu_granule(n2)
+    assert g in (32, 64, 128) and (n2 // 2) % g == 0
+    wg = torch.arange(n2 * dim, dtype=torch.float32).reshape(n2, dim)
+    b = torch.arange(n2, dtype=torch.float32)
+    wp, bp = ops.pack_geglu_weight(wg, b)
+    inner = n2 // 2
+    for j in (0, g - 1, g, 3 * g + 5, inner - 1):  # value row j and gate row j land in the same 2g-row tile
+        tile, off = divmod(j, g)
+        assert torch.equal(wp[tile * 2 * g + off], wg[j]) and torch.equal(wp[tile * 2 * g + g + off], wg[inner + j])
+        assert bp[tile * 2 * g + off] == b[j] and bp[tile * 2 * g + g + off] == b[inner + j]
