@@ -109,8 +109,10 @@ int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream);
 int mimo_im2col3x3(const void* x, void* col, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride,
                    int32_t upshift, int32_t pad_lo, int64_t ldcol, int32_t dtype, void* stream);
 
-/* GroupNorm over channels-last activations, optional SiLU, optional two-source virtual concat.
- * stats: workspace of 2 * n * groups floats. Replaces InflatedGroupNorm / nn.GroupNorm + F.silu
+/* GroupNorm over channels-last activations, optional SiLU, optional two-source virtual concat: ONE pass over HBM
+ * (each image slab stays in registers between the statistics and the normalisation) and deterministic (fixed-order
+ * reductions, no floating-point atomics). stats: workspace of mimo_groupnorm_workspace_bytes(p) bytes, 16-byte aligned,
+ * contents irrelevant. Replaces InflatedGroupNorm / nn.GroupNorm + F.silu
  * (src/models/resnet.py:20-28, 220-221, 231, 237; transformer_3d.py:58-60,124; motion_module.py:119-121,156). */
 typedef struct {
   const void* x0;
@@ -127,6 +129,8 @@ typedef struct {
   int32_t dtype;
 } mimo_groupnorm_params;
 int mimo_groupnorm(const mimo_groupnorm_params* p, void* stream);
+/* bytes of `stats` workspace mimo_groupnorm needs for these sizes (pointers in *p are ignored); < 0 on bad sizes */
+int64_t mimo_groupnorm_workspace_bytes(const mimo_groupnorm_params* p);
 
 /* LayerNorm over the last dim; optional additive per-frame vector AFTER the affine (the motion module's
  * sinusoidal positional encoding): out[r] = LN(x[r]) * gamma + beta + pe[pe_frame_offset + (r / rows_per_frame) % frames]

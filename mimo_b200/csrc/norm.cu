@@ -10,7 +10,16 @@
 namespace mimo {
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm
+// GroupNorm(+SiLU): ONE pass over HBM (one read, one write), deterministic.
+//
+// A work item is a slab of P*ITERS pixels x all C channels of one image; the slab stays in REGISTERS between the
+// statistics phase and the normalise phase. Per item: load slab -> per-(slab, group) partial (sum, sumsq), reduced
+// inside the block in a fixed order -> published to part[image][slab][group] -> arrive on the image's counter ->
+// wait until all slabs of the image have arrived -> every block sums the image's partials in the same fixed order
+// (bit-identical run to run and block to block; no floating-point atomics anywhere) -> normalise, affine, SiLU, store.
+// Blocks walk the items image-major (item = block + k * grid), so the slabs of one image are in flight together; the
+// launch is cooperative (all blocks co-resident), which makes the per-image wait deadlock-free: the lowest
+// unfinished image only ever waits on blocks whose earlier items are complete.
 // ------------------------------------------------------------------------------------------------
 struct GnArgs {
   const void* x0;
@@ -18,11 +27,13 @@ struct GnArgs {
   const void* gamma;
   const void* beta;
   void* out;
-  float* stats;  // [n][groups][2] = (sum, sumsq)
+  float* part;        // [n][bpi][groups][2] = (sum, sumsq) per slab
+  unsigned* arrived;  // [n] slabs of the image whose partials are published (zeroed by the launcher)
   int c0, c1, C, hw, groups, cpg;
-  int vecs;      // C / 8
-  int P;         // pixels processed per block iteration
-  int pix_per_block;
+  int vecs;  // C / 8
+  int P;     // pixels processed side by side by one block
+  int bpi;   // slabs (work items) per image
+  int n;
   float eps;
   int silu;
 };
@@ -37,128 +48,200 @@ __device__ __forceinline__ uint4 gn_load(const GnArgs& a, long long pix, int cv)
   return *reinterpret_cast<const uint4*>(static_cast<const typename C::T*>(a.x1) + pix * a.c1 + (ch - a.c0));
 }
 
-// pass 1: per-(image, group) sum and sum of squares
-template <bool kBf16>
-__global__ void __launch_bounds__(1024) gn_stats_kernel(GnArgs a) {
+constexpr int kGnMaxThreads = 320;
+
+template <bool kBf16, int ITERS>
+__global__ void __launch_bounds__(kGnMaxThreads, ITERS >= 16 ? 1 : 2) gn_onepass_kernel(GnArgs a) {
   using C = Cvt<kBf16>;
-  __shared__ float s_sum[64], s_sq[64];
-  const int n = blockIdx.y;
-  const int cv = threadIdx.x % a.vecs;
-  const int pl = threadIdx.x / a.vecs;
+  __shared__ float4 s_red[kGnMaxThreads];  // per-thread (sumA, sqA, sumB, sqB)
+  __shared__ float s_tot[4][128];          // up to 4 partial sums of (group, {sum, sumsq})
+  __shared__ float s_mean[64], s_rstd[64];
+  const int tid = threadIdx.x;
+  const int cv = tid % a.vecs;
+  const int pl = tid / a.vecs;
   const bool active = pl < a.P;
-  for (int i = threadIdx.x; i < a.groups; i += blockDim.x) {
-    s_sum[i] = 0.f;
-    s_sq[i] = 0.f;
-  }
-  __syncthreads();
   const int ch0 = cv * 8;
   const int gA = ch0 / a.cpg;
   int split = (gA + 1) * a.cpg - ch0;  // channels [0, split) of this vector belong to gA, the rest to gA + 1
   if (split > 8) split = 8;
-  float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+  const int ppb = a.P * ITERS;
+  const float inv_cnt = 1.0f / (static_cast<float>(a.hw) * a.cpg);
+  // gamma / beta of this thread's 8 channels, packed (unpacked on use: 8 registers instead of 16)
+  uint32_t wg[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
   if (active) {
-    const int p_begin = blockIdx.x * a.pix_per_block;
-    int p_end = p_begin + a.pix_per_block;
-    if (p_end > a.hw) p_end = a.hw;
-    for (int p = p_begin + pl; p < p_end; p += a.P) {
-      const uint4 u = gn_load<kBf16>(a, static_cast<long long>(n) * a.hw + p, cv);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-      float f[8];
+    const uint4 ug = *reinterpret_cast<const uint4*>(static_cast<const typename C::T*>(a.gamma) + ch0);
+    const uint4 ub = *reinterpret_cast<const uint4*>(static_cast<const typename C::T*>(a.beta) + ch0);
+    wg[0] = ug.x, wg[1] = ug.y, wg[2] = ug.z, wg[3] = ug.w;
+    wb[0] = ub.x, wb[1] = ub.y, wb[2] = ub.z, wb[3] = ub.w;
+  }
+  const int g2 = a.groups * 2;
+  const int total = a.n * a.bpi;
+#pragma unroll 1
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int n = item / a.bpi;
+    const int pb = item - n * a.bpi;
+    const int p0 = pb * ppb + pl;
+    const long long pix0 = static_cast<long long>(n) * a.hw;
+    // ---- load the slab (all loads in flight before the first use) ----
+    uint4 u[ITERS];
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int p = p0 + i * a.P;
+      u[i] = (active && p < a.hw) ? gn_load<kBf16>(a, pix0 + p, cv) : make_uint4(0, 0, 0, 0);
+    }
+    // ---- partial statistics of the slab ----
+    float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 t = C::unpack(w[j]);
-        f[2 * j] = t.x;
-        f[2 * j + 1] = t.y;
+        if (2 * j < split) sA += t.x, qA += t.x * t.x; else sB += t.x, qB += t.x * t.x;
+        if (2 * j + 1 < split) sA += t.y, qA += t.y * t.y; else sB += t.y, qB += t.y * t.y;
+      }
+    }
+    s_red[tid] = make_float4(sA, qA, sB, qB);
+    __syncthreads();
+    for (int g = tid; g < a.groups; g += blockDim.x) {  // fixed order: vectors touching group g, then pixel lanes
+      const int v_lo = (g * a.cpg) >> 3;
+      const int v_hi = ((g + 1) * a.cpg - 1) >> 3;
+      float s = 0.f, q = 0.f;
+      for (int v = v_lo; v <= v_hi; ++v) {
+        const bool as_a = (v * 8) / a.cpg == g;  // this vector's first group is g (else g is its second group)
+        for (int l = 0; l < a.P; ++l) {
+          const float4 r = s_red[l * a.vecs + v];
+          s += as_a ? r.x : r.z;
+          q += as_a ? r.y : r.w;
+        }
+      }
+      float* dst = a.part + (static_cast<long long>(item) * a.groups + g) * 2;
+      __stcg(dst, s);
+      __stcg(dst + 1, q);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();  // release: everything the block published (ordered before the barrier) precedes the arrival
+      atomicAdd(a.arrived + n, 1u);
+      unsigned seen;
+      unsigned spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.arrived + n) : "memory");
+        if (seen >= static_cast<unsigned>(a.bpi)) break;
+        __nanosleep(40);
+        if (++spins > (1u << 24)) {  // seconds: a scheduling bug must trap, never hang the GPU
+          printf("mimo: groupnorm image barrier timeout (block %d image %d: %u of %d)\n", blockIdx.x, n, seen, a.bpi);
+          __trap();
+        }
+      } while (true);
+    }
+    __syncthreads();
+    // ---- image totals: the same fixed order in every block -> bit-identical statistics everywhere ----
+    {
+      const int parts = a.bpi >= 16 ? 4 : 1;  // a function of the shape only: the summation order never varies
+      const float* src = a.part + static_cast<long long>(n) * a.bpi * g2;
+      for (int idx = tid; idx < parts * g2; idx += blockDim.x) {
+        const int k = idx % g2, part = idx / g2;
+        float acc = 0.f;
+        for (int b = part; b < a.bpi; b += parts) acc += __ldcg(src + static_cast<long long>(b) * g2 + k);
+        s_tot[part][k] = acc;
+      }
+      __syncthreads();
+      for (int g = tid; g < a.groups; g += blockDim.x) {
+        float s = 0.f, q = 0.f;
+        for (int part = 0; part < parts; ++part) {
+          s += s_tot[part][2 * g];
+          q += s_tot[part][2 * g + 1];
+        }
+        const float mean = s * inv_cnt;
+        float var = q * inv_cnt - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        s_mean[g] = mean;
+        s_rstd[g] = rsqrtf(var + a.eps);
+      }
+      __syncthreads();
+    }
+    // ---- normalise + affine (+ SiLU) from registers, store ----
+    if (active) {
+      const float mA = s_mean[gA], rA = s_rstd[gA];
+      const float mB = split < 8 ? s_mean[gA + 1] : 0.f, rB = split < 8 ? s_rstd[gA + 1] : 0.f;
+      float sc[8], sh[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 gg = C::unpack(wg[j]);
+        const float2 bb = C::unpack(wb[j]);
+        const float m0 = 2 * j < split ? mA : mB, r0 = 2 * j < split ? rA : rB;
+        const float m1 = 2 * j + 1 < split ? mA : mB, r1 = 2 * j + 1 < split ? rA : rB;
+        sc[2 * j] = r0 * gg.x;
+        sh[2 * j] = bb.x - m0 * r0 * gg.x;
+        sc[2 * j + 1] = r1 * gg.y;
+        sh[2 * j + 1] = bb.y - m1 * r1 * gg.y;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < split) {
-          sA += f[j];
-          qA += f[j] * f[j];
-        } else {
-          sB += f[j];
-          qB += f[j] * f[j];
+      for (int i = 0; i < ITERS; ++i) {
+        const int p = p0 + i * a.P;
+        if (p < a.hw) {
+          const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 t = C::unpack(w[j]);
+            f[2 * j] = fmaf(t.x, sc[2 * j], sh[2 * j]);
+            f[2 * j + 1] = fmaf(t.y, sc[2 * j + 1], sh[2 * j + 1]);
+          }
+          if (a.silu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+          }
+          uint4 o;
+          o.x = C::pack(f[0], f[1]);
+          o.y = C::pack(f[2], f[3]);
+          o.z = C::pack(f[4], f[5]);
+          o.w = C::pack(f[6], f[7]);
+          *reinterpret_cast<uint4*>(static_cast<typename C::T*>(a.out) + (pix0 + p) * a.C + ch0) = o;
         }
       }
     }
-    atomicAdd(&s_sum[gA], sA);
-    atomicAdd(&s_sq[gA], qA);
-    if (split < 8) {
-      atomicAdd(&s_sum[gA + 1], sB);
-      atomicAdd(&s_sq[gA + 1], qB);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < a.groups; i += blockDim.x) {
-    atomicAdd(&a.stats[(static_cast<long long>(n) * a.groups + i) * 2 + 0], s_sum[i]);
-    atomicAdd(&a.stats[(static_cast<long long>(n) * a.groups + i) * 2 + 1], s_sq[i]);
+    __syncthreads();  // s_red / s_tot / s_mean are reused by the next item
   }
 }
 
-// pass 2: normalise + affine (+ SiLU), dense [n, hw, C] output (this is also where a virtual concat lands)
-template <bool kBf16>
-__global__ void __launch_bounds__(1024) gn_apply_kernel(GnArgs a) {
-  using C = Cvt<kBf16>;
-  const int n = blockIdx.y;
-  const int cv = threadIdx.x % a.vecs;
-  const int pl = threadIdx.x / a.vecs;
-  if (pl >= a.P) return;
-  const int ch0 = cv * 8;
-  const float inv_cnt = 1.0f / (static_cast<float>(a.hw) * a.cpg);
-  float sc[8], sh[8];
-  {
-    const uint4 ug = *reinterpret_cast<const uint4*>(static_cast<const typename C::T*>(a.gamma) + ch0);
-    const uint4 ub = *reinterpret_cast<const uint4*>(static_cast<const typename C::T*>(a.beta) + ch0);
-    const uint32_t wg[4] = {ug.x, ug.y, ug.z, ug.w};
-    const uint32_t wb[4] = {ub.x, ub.y, ub.z, ub.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 g2 = C::unpack(wg[j]);
-      const float2 b2 = C::unpack(wb[j]);
-      sc[2 * j] = g2.x;
-      sc[2 * j + 1] = g2.y;
-      sh[2 * j] = b2.x;
-      sh[2 * j + 1] = b2.y;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (ch0 + j) / a.cpg;
-      const float s = a.stats[(static_cast<long long>(n) * a.groups + g) * 2 + 0];
-      const float q = a.stats[(static_cast<long long>(n) * a.groups + g) * 2 + 1];
-      const float mean = s * inv_cnt;
-      float var = q * inv_cnt - mean * mean;
-      var = var < 0.f ? 0.f : var;
-      const float rstd = rsqrtf(var + a.eps);
-      sh[j] = sh[j] - mean * rstd * sc[j];
-      sc[j] = rstd * sc[j];
-    }
+static int g_gn_max_iters = 8;  // 8: two 40 KB slabs per SM in different phases; 16 (test hook): one 80 KB slab
+// launch geometry shared by mimo_groupnorm and mimo_groupnorm_workspace_bytes
+struct GnPlan {
+  int vecs, P, iters, bpi, threads;
+};
+static GnPlan gn_plan(int n, int hw, int C) {
+  GnPlan pl;
+  pl.vecs = C / 8;
+  pl.P = kGnMaxThreads / pl.vecs;
+  if (pl.P < 1) pl.P = 1;
+  if (pl.P > hw) pl.P = hw;
+  pl.threads = ((pl.vecs * pl.P + 31) / 32) * 32;
+  int iters = g_gn_max_iters;
+  const long long want = 2LL * num_sms();  // enough slabs to fill the machine twice, if the tensor allows it
+  while (iters > 1 && (pl.P * (iters >> 1) >= hw || static_cast<long long>(n) * div_up(hw, pl.P * iters) < want)) iters >>= 1;
+  pl.iters = iters;
+  pl.bpi = static_cast<int>(div_up(hw, pl.P * iters));
+  return pl;
+}
+
+template <bool kBf16, int ITERS>
+static cudaError_t gn_launch(const GnArgs& a, int threads, cudaStream_t st) {
+  static int occ = 0;  // per (dtype, ITERS) instantiation; the block size only ever shrinks below kGnMaxThreads
+  if (!occ) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_onepass_kernel<kBf16, ITERS>, kGnMaxThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
   }
-  const int p_begin = blockIdx.x * a.pix_per_block;
-  int p_end = p_begin + a.pix_per_block;
-  if (p_end > a.hw) p_end = a.hw;
-  for (int p = p_begin + pl; p < p_end; p += a.P) {
-    const long long pix = static_cast<long long>(n) * a.hw + p;
-    const uint4 u = gn_load<kBf16>(a, pix, cv);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = C::unpack(w[j]);
-      f[2 * j] = t.x;
-      f[2 * j + 1] = t.y;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      f[j] = f[j] * sc[j] + sh[j];
-      if (a.silu) f[j] = silu_f(f[j]);
-    }
-    uint4 o;
-    o.x = C::pack(f[0], f[1]);
-    o.y = C::pack(f[2], f[3]);
-    o.z = C::pack(f[4], f[5]);
-    o.w = C::pack(f[6], f[7]);
-    *reinterpret_cast<uint4*>(static_cast<typename C::T*>(a.out) + pix * a.C + ch0) = o;
-  }
+  const long long items = static_cast<long long>(a.n) * a.bpi;
+  long long grid = static_cast<long long>(occ) * num_sms();
+  if (grid > items) grid = items;
+  GnArgs args = a;
+  void* kargs[] = {&args};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(gn_onepass_kernel<kBf16, ITERS>),
+                                     dim3(static_cast<unsigned>(grid)), dim3(threads), kargs, 0, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -371,54 +454,71 @@ static void launch_ln5(int L, const void* x, const void* gamma, const void* beta
 
 using namespace mimo;
 
-extern "C" int mimo_groupnorm(const mimo_groupnorm_params* p, void* stream) {
-  if (!p || !p->x0 || !p->gamma || !p->beta || !p->out || !p->stats)
-    return set_error(MIMO_ERR_ARG, "mimo_groupnorm: null pointer");
+static int gn_check(const mimo_groupnorm_params* p, int* Cout) {
+  if (!p) return set_error(MIMO_ERR_ARG, "mimo_groupnorm: null params");
   const int c1 = p->x1 ? p->c1 : 0;
   const int C = p->c0 + c1;
   if (p->n <= 0 || p->hw <= 0 || C <= 0 || p->groups <= 0 || p->groups > 64)
     return set_error(MIMO_ERR_ARG, "mimo_groupnorm: bad sizes");
-  if ((p->c0 % 8) || (c1 % 8) || (C % p->groups) || (C / 8 > 1024))
-    return set_error(MIMO_ERR_ARG, "mimo_groupnorm: channels must be multiples of 8 and divisible by groups");
-  {
-    const int cpg = C / p->groups;  // an 8-channel vector may straddle at most two groups
-    if (!(cpg >= 8 || cpg == 4)) return set_error(MIMO_ERR_ARG, "mimo_groupnorm: channels per group must be 4 or >= 8");
-  }
+  if ((p->c0 % 8) || (c1 % 8) || (C % p->groups) || (C / 8 > kGnMaxThreads))
+    return set_error(MIMO_ERR_ARG, "mimo_groupnorm: channels must be multiples of 8, divisible by groups, <= 2560");
+  const int cpg = C / p->groups;  // an 8-channel vector may straddle at most two groups
+  if (!(cpg >= 8 || cpg == 4)) return set_error(MIMO_ERR_ARG, "mimo_groupnorm: channels per group must be 4 or >= 8");
+  *Cout = C;
+  return MIMO_OK;
+}
+
+extern "C" int mimo_debug_gn_max_iters(int iters) {
+  if (iters == 16 || iters == 8 || iters == 4 || iters == 2 || iters == 1) g_gn_max_iters = iters;
+  return g_gn_max_iters;
+}
+
+extern "C" int64_t mimo_groupnorm_workspace_bytes(const mimo_groupnorm_params* p) {
+  int C = 0;
+  if (int rc = gn_check(p, &C)) return rc;
+  const GnPlan pl = gn_plan(p->n, p->hw, C);
+  // per-slab partials + one arrival counter per image (rounded up to 16 bytes)
+  return static_cast<int64_t>(p->n) * pl.bpi * p->groups * 2 * sizeof(float) + ((static_cast<int64_t>(p->n) * 4 + 15) / 16) * 16;
+}
+
+extern "C" int mimo_groupnorm(const mimo_groupnorm_params* p, void* stream) {
+  int C = 0;
+  if (int rc = gn_check(p, &C)) return rc;
+  if (!p->x0 || !p->gamma || !p->beta || !p->out || !p->stats)
+    return set_error(MIMO_ERR_ARG, "mimo_groupnorm: null pointer");
   if (int rc = ensure_device()) return rc;
+  const GnPlan pl = gn_plan(p->n, p->hw, C);
   GnArgs a;
   a.x0 = p->x0;
   a.x1 = p->x1;
   a.gamma = p->gamma;
   a.beta = p->beta;
   a.out = p->out;
-  a.stats = p->stats;
+  a.part = p->stats;
+  a.arrived = reinterpret_cast<unsigned*>(p->stats + static_cast<int64_t>(p->n) * pl.bpi * p->groups * 2);
   a.c0 = p->c0;
-  a.c1 = c1;
+  a.c1 = p->x1 ? p->c1 : 0;
   a.C = C;
   a.hw = p->hw;
   a.groups = p->groups;
   a.cpg = C / p->groups;
-  a.vecs = C / 8;
-  a.P = 256 / a.vecs;
-  if (a.P < 1) a.P = 1;
-  if (a.P > p->hw) a.P = p->hw;
-  int iters = 16;
-  a.pix_per_block = a.P * iters;
+  a.vecs = pl.vecs;
+  a.P = pl.P;
+  a.bpi = pl.bpi;
+  a.n = p->n;
   a.eps = p->eps;
   a.silu = p->silu;
-  const int threads = ((a.vecs * a.P + 31) / 32) * 32;
-  dim3 grid(div_up(p->hw, a.pix_per_block), p->n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(p->stats, 0, sizeof(float) * 2 * p->n * p->groups, st);
+  cudaError_t e = cudaMemsetAsync(a.arrived, 0, sizeof(unsigned) * p->n, st);
   if (e != cudaSuccess) return set_cuda_error("groupnorm memset", e);
-  if (p->dtype == MIMO_BF16) {
-    gn_stats_kernel<true><<<grid, threads, 0, st>>>(a);
-    gn_apply_kernel<true><<<grid, threads, 0, st>>>(a);
-  } else {
-    gn_stats_kernel<false><<<grid, threads, 0, st>>>(a);
-    gn_apply_kernel<false><<<grid, threads, 0, st>>>(a);
+  const bool bf = p->dtype == MIMO_BF16;
+  switch (pl.iters) {
+    case 16: e = bf ? gn_launch<true, 16>(a, pl.threads, st) : gn_launch<false, 16>(a, pl.threads, st); break;
+    case 8: e = bf ? gn_launch<true, 8>(a, pl.threads, st) : gn_launch<false, 8>(a, pl.threads, st); break;
+    case 4: e = bf ? gn_launch<true, 4>(a, pl.threads, st) : gn_launch<false, 4>(a, pl.threads, st); break;
+    case 2: e = bf ? gn_launch<true, 2>(a, pl.threads, st) : gn_launch<false, 2>(a, pl.threads, st); break;
+    default: e = bf ? gn_launch<true, 1>(a, pl.threads, st) : gn_launch<false, 1>(a, pl.threads, st); break;
   }
-  e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("groupnorm launch", e);
   return MIMO_OK;
 }

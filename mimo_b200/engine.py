@@ -252,6 +252,10 @@ class UNetEngine:
         hcur = ops.gemm(hcur, m["pin"][0], bias=m["pin"][1])
         C = hcur.shape[1]
         rank, world, group = self.shard
+        if f * world > m["attn"][0]["pe"].shape[0]:
+            # the reference fails here with a shape error (motion_module.py:277-279: x + pe[:, :x.size(1)])
+            raise L.MimoError(f"{f * world} frames in a window exceed temporal_position_encoding_max_len="
+                              f"{m['attn'][0]['pe'].shape[0]}")
         for a in m["attn"]:
             if world == 1:
                 nh = ops.layernorm(hcur, *a["ln"], pe=a["pe"], rows_per_frame=hw, frames=f)
@@ -451,7 +455,6 @@ class UNetEngine:
             g["sample"] = sample.clone()
             g["emb"] = emb.clone()
             g["pose"] = pose_nhwc.clone() if pose_nhwc is not None else None
-            g["pose_src"] = None
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             l0 = ops.launches()
@@ -463,10 +466,9 @@ class UNetEngine:
         g["sample"].copy_(sample)
         g["emb"].copy_(emb)
         if pose_nhwc is not None:
-            src = (pose_nhwc.data_ptr(), pose_nhwc._version)
-            if g["pose_src"] != src:  # the window's pose features change once per clip, not per step
-                g["pose"].copy_(pose_nhwc)
-                g["pose_src"] = src
+            # always copied: neither data_ptr nor torch's version counter identify the CONTENT of a tensor that is
+            # written through raw pointers and recycled by the caching allocator (a stale-pose replay otherwise)
+            g["pose"].copy_(pose_nhwc)
         g["graph"].replay()
         ops.add_launches(g["launches"])
         return g["out"]

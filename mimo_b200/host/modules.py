@@ -143,7 +143,7 @@ class _UNetBase(_EngineModel):
     _out_head = False
 
     def _init_unet(self, block_out_channels, layers_per_block, cross_attention_dim, attention_head_dim, norm_num_groups,
-                   norm_eps, in_channels, out_channels, extra: dict):
+                   norm_eps, in_channels, out_channels, extra: dict, motion_max_len: int = 32):
         if isinstance(attention_head_dim, (tuple, list)):
             if len(set(attention_head_dim)) != 1:
                 raise NotImplementedError("per-level attention_head_dim is not used by the reference's SD1.5 config")
@@ -157,7 +157,8 @@ class _UNetBase(_EngineModel):
                                 norm_num_groups=norm_num_groups, norm_eps=norm_eps, in_channels=in_channels,
                                 out_channels=out_channels, motion=self._motion, out_head=self._out_head)
         self._materialise(schema.unet_schema(block_out_channels, layers_per_block, cross_attention_dim, in_channels,
-                                             out_channels, motion=self._motion, out_head=self._out_head))
+                                             out_channels, motion=self._motion, out_head=self._out_head,
+                                             motion_max_len=motion_max_len))
         self._ref_mode: Optional[str] = None
         self._ref_cfg = False
 
@@ -262,7 +263,7 @@ class UNet3DConditionModel(_UNetBase):
         self._motion_max_len = mk.get("temporal_position_encoding_max_len", 32)
         self._init_unet(block_out_channels, layers_per_block, cross_attention_dim, attention_head_dim, norm_num_groups,
                         norm_eps, 8, out_channels,  # in_channels is forced to 8 (unet_3d_edit_bkfill.py:88)
-                        dict(sample_size=sample_size))
+                        dict(sample_size=sample_size), motion_max_len=self._motion_max_len)
         self._xattn_key = None
 
     @classmethod

@@ -54,17 +54,37 @@ def pil_to_tensor(images, height: int, width: int, normalize: bool, scale_factor
 def _dedupe_images(images) -> "tuple[list, torch.Tensor]":
     """Indices of the first occurrence of every distinct image (by size, mode and pixel bytes) and, per image, the
     index of its representative among those: animate mode passes one identical white background per frame
-    (run_animate.py:174-177) and the VAE should see it once."""
-    import zlib
-    first, inverse, seen = [], [], {}
+    (run_animate.py:174-177) and the VAE should see it once. A hash hit is confirmed byte for byte, so two different
+    frames can never share latents."""
+    import hashlib
+    first, inverse, seen, raws = [], [], {}, []
     for i, im in enumerate(images):
         raw = im.tobytes()
-        key = (im.size, im.mode, len(raw), zlib.crc32(raw), zlib.adler32(raw))
-        if key not in seen:
-            seen[key] = len(first)
+        key = (im.size, im.mode, hashlib.blake2b(raw, digest_size=16).digest())
+        j = seen.get(key)
+        if j is not None and raws[j] != raw:  # a genuine 128-bit collision: treat as distinct
+            j = None
+        if j is None:
+            j = len(first)
+            seen.setdefault(key, j)
             first.append(i)
-        inverse.append(seen[key])
+            raws.append(raw)
+        inverse.append(j)
     return first, torch.tensor(inverse, dtype=torch.long)
+
+
+def _randn_tensor(shape, generator, device: torch.device, dtype) -> torch.Tensor:
+    """diffusers.utils.torch_utils.randn_tensor [3P] (pipeline :175-177): the draw happens on the generator's device
+    (CPU generator -> CPU draw in the target dtype, then moved: this is what defines seed parity); a list of
+    generators draws one batch element each; no generator draws on the execution device."""
+    gens = generator if isinstance(generator, (list, tuple)) else [generator]
+    gdev = gens[0].device if gens[0] is not None else device
+    if gdev.type != device.type and gdev.type != "cpu":
+        raise ValueError(f"Cannot generate a {device} tensor from a generator of type {gdev.type}.")
+    if isinstance(generator, (list, tuple)):
+        one = (1,) + tuple(shape[1:])
+        return torch.cat([torch.randn(one, generator=g, device=gdev, dtype=dtype) for g in generator], 0).to(device)
+    return torch.randn(shape, generator=generator, device=gdev, dtype=dtype).to(device)
 
 
 class Pose2VideoPipeline:
@@ -142,9 +162,9 @@ class Pose2VideoPipeline:
             raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
                              f"effective batch size of {batch_size}.")
         if latents is None:
-            # randn_tensor [3P]: a CPU generator draws on the CPU in the target dtype, then moves (pipeline :175-177)
-            gdev = "cpu" if generator is None or generator.device.type == "cpu" else device
-            latents = torch.randn(shape, generator=generator, device=gdev, dtype=dtype)
+            latents = _randn_tensor(shape, generator, torch.device(device), dtype)
+        else:
+            latents = latents.to(device)  # pipeline :179
         return latents * self.scheduler.init_noise_sigma
 
     # ------------------------------------------------------------------------------------------------
@@ -154,6 +174,9 @@ class Pose2VideoPipeline:
         :424-426, :435-437, :446-453 before anything touches the device)."""
         pin = lambda t: t.contiguous().pin_memory() if torch.cuda.is_available() else t.contiguous()
         bks = list(vid_bk_images)
+        if len(bks) != video_length or len(pose_images) != video_length:
+            raise ValueError(f"video_length={video_length} but {len(pose_images)} pose images and {len(bks)} background "
+                             "images were passed (pipeline :435-453 indexes both per frame)")
         first, inverse = _dedupe_images(bks)  # identical background frames are converted, copied and encoded once
         return {
             "clip_pixels": pin(self._clip_pixels(ref_image)),

@@ -37,6 +37,11 @@ class DDIMScheduler:
             betas = 1 - alphas
         if clip_sample:
             raise NotImplementedError("clip_sample=True is not used by the reference and not implemented")
+        if prediction_type != "v_prediction":
+            # the fused CFG+DDIM kernel and step() implement the reference's shipped parameterisation only
+            # (configs/inference/inference_v2.yaml:24-33); silently running v-prediction for "epsilon" would be wrong
+            raise NotImplementedError(f"prediction_type={prediction_type!r}: only 'v_prediction' (the reference's "
+                                      "inference_v2.yaml) is implemented")
         self.betas = betas
         self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
         self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
@@ -63,6 +68,31 @@ class DDIMScheduler:
 
     def scale_model_input(self, sample, timestep=None):
         return sample
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0,
+             use_clipped_model_output: bool = False, generator=None, variance_noise=None, return_dict: bool = True,
+             **unused):
+        """diffusers DDIMScheduler.step [3P] for v-prediction, eta = 0 (pipeline :551-553): tensor in, tensor out, in
+        the dtype / on the device of `sample`. The engine's own sampler uses the fused kernel (step_coefficients);
+        this method exists so that the reference's unmodified pipeline file runs over this scheduler."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating "
+                             "the scheduler")
+        if eta != 0.0 or use_clipped_model_output or variance_noise is not None:
+            raise NotImplementedError("eta != 0 / clipped model output / variance noise are outside the reference's "
+                                      "shipped configuration")
+        t = int(timestep)
+        prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_p = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
+        b_t = 1 - a_t
+        x0 = (a_t ** 0.5) * sample - (b_t ** 0.5) * model_output
+        eps = (a_t ** 0.5) * model_output + (b_t ** 0.5) * sample
+        direction = (1 - a_p) ** 0.5 * eps  # std_dev_t = 0 at eta = 0
+        prev = a_p ** 0.5 * x0 + direction
+        if not return_dict:
+            return (prev,)
+        return SimpleNamespace(prev_sample=prev, pred_original_sample=x0)
 
     def step_coefficients(self, t: int):
         """(sqrt(abar_t), sqrt(1 - abar_t), sqrt(abar_prev), sqrt(1 - abar_prev)); prev_t = t - T // N (NOT the next

@@ -159,20 +159,23 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int,
     c1 = x1.shape[1] if x1 is not None else 0
     if out is None:
         out = torch.empty((n * hw, c0 + c1), dtype=x0.dtype, device=x0.device)
-    if stats is None:
-        stats = torch.empty((n * groups * 2,), dtype=torch.float32, device=x0.device)
-    assert x0.is_contiguous() and out.is_contiguous() and stats.numel() >= n * groups * 2
     p = L.GroupNormParams()
     p.x0, p.c0 = _ptr(x0), c0
     p.x1, p.c1 = _ptr(x1), c1
     p.gamma, p.beta = _ptr(gamma), _ptr(beta)
     p.out = _ptr(out)
-    p.stats = _ptr(stats)
     p.n, p.hw, p.groups = n, hw, groups
     p.eps = float(eps)
     p.silu = int(bool(silu))
     p.dtype = _dt(x0)
-    with _Call("groupnorm", 2, 0.0, 2.0 * 2 * out.numel()):  # algorithmic: one read + one write
+    need = L.load().mimo_groupnorm_workspace_bytes(C.byref(p))
+    if need < 0:
+        L.check(int(need), "mimo_groupnorm_workspace_bytes")
+    if stats is None:
+        stats = torch.empty(((need + 3) // 4,), dtype=torch.float32, device=x0.device)
+    assert x0.is_contiguous() and out.is_contiguous() and stats.numel() * 4 >= need
+    p.stats = _ptr(stats)
+    with _Call("groupnorm", 1, 0.0, 2.0 * 2 * out.numel()):  # algorithmic: one read + one write
         L.check(L.load().mimo_groupnorm(C.byref(p), _stream()), "mimo_groupnorm")
     return out
 

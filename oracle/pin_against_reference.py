@@ -194,7 +194,9 @@ def main():
     small = O.UNetConfig(block_out_channels=(128, 256, 512, 512))
     r1 = unet_case(small, f=4, hw=16, seed=100)
     small_vae = O.VAEConfig(block_out_channels=(32, 64, 128, 128))
-    p1 = pipeline_case(small, small_vae, F=1, size=256, steps=2, seed=200)       # BASELINE config 1 shape
+    # BASELINE config 1 shape; the VAE at full sd-vae-ft-mse width so that the engine (GroupNorm needs >= 4 channels
+    # per group) can consume the fixture in tests/test_parity_gpu.py
+    p1 = pipeline_case(small, O.VAEConfig(), F=1, size=256, steps=2, seed=200)
     p2 = pipeline_case(small, small_vae, F=26, size=64, steps=2, seed=300)       # > 24 frames: 2 windows
     if args.full:
         rfull = unet_case(O.UNetConfig(), f=2, hw=16, seed=400)
@@ -202,7 +204,8 @@ def main():
         (gold / "integer_tables.json").write_text(json.dumps(tables, indent=1))
         torch.save({"cfg": list(small.block_out_channels), "seed": 100, "f": 4, "hw": 16,
                     "out": r1["out"].half()}, gold / "unet_small_read.pt")
-        torch.save({"seed": 200, "F": 1, "size": 256, "steps": 2, "latents": p1["latents"].half(),
+        torch.save({"seed": 200, "F": 1, "size": 256, "steps": 2, "vae_widths": list(O.VAEConfig().block_out_channels),
+                    "latents": p1["latents"].half(),
                     "videos_mean": float(p1["videos"].mean()), "videos": p1["videos"][:, :, :, ::8, ::8].half()},
                    gold / "pipeline_cfg1.pt")
         if args.full:
