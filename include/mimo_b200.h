@@ -41,7 +41,7 @@ const char* mimo_last_error(void);
 /* 0 if device `dev` is sm_100; MIMO_ERR_DEVICE otherwise (also when there is no CUDA device at all). */
 int mimo_device_check(int dev);
 /* sizeof() of the parameter structs as compiled into the library (0 epilogue, 1 gemm, 2 conv3x3, 3 groupnorm,
- * 4 attn, 5 attn_temporal): lets a binding verify its struct mirrors before the first call. */
+ * 4 attn, 5 attn_temporal, 6 exchange): lets a binding verify its struct mirrors before the first call. */
 int mimo_abi_sizeof(int which);
 
 /* Fused epilogue shared by GEMM and conv:  out = act((acc + bias[c] + rowvec[row / rows_per_group][c]
@@ -188,6 +188,41 @@ typedef struct {
   int32_t dtype;
 } mimo_attn_temporal_params;
 int mimo_attn_temporal(const mimo_attn_temporal_params* p, void* stream);
+
+/* Frame-shard <-> pixel-shard exchange of the motion module over NVLink PEER MEMORY (one process per GPU, G GPUs in a
+ * frame group, this GPU is member r). Each GPU pulls its share directly from its peers' source buffers (IPC-mapped
+ * device pointers, see mimo_peer_*), synchronised by epoch flags in peer memory; no collective library and no host
+ * work on the data path, CUDA-graph capturable. Tokens are channels-last rows of C elements.
+ *   mode 0 (frames -> pixels): src on every peer is [b, fl, hw, C] (its fl frames of the window); dst becomes
+ *           [b, G*fl, hw/G, C]: ALL frames of this GPU's pixel shard  (before VersatileAttention, motion_module.py:353-390)
+ *   mode 1 (pixels -> frames): src on every peer is [b, G*fl, hw/G, C]; dst becomes [b, fl, hw, C] (+ residual, same
+ *           layout as dst): the motion module's output for this GPU's frames (motion_module.py:181-183)
+ *   mode 2 (all-gather): src on every peer is [b*fl*hw, C]; dst becomes [G, b*fl*hw, C]
+ * peer_src[s] / peer_ready[s]: peer s's source buffer / its array of MIMO_MAX_PEERS uint32 flags (zero-initialised once),
+ * as mapped into THIS process; index r is this GPU's own buffer / flags. ctl: two uint32 of local device memory,
+ * initialised to {1, 0} once per group, never touched by the host afterwards. All members must issue the same sequence
+ * of exchanges. A peer that does not show up within timeout_ms (0 = 30 s) traps the kernel. */
+#define MIMO_MAX_PEERS 8
+typedef struct {
+  const void* peer_src[MIMO_MAX_PEERS];
+  void* peer_ready[MIMO_MAX_PEERS];
+  void* ctl;
+  void* dst;
+  const void* residual; /* mode 1 only, or NULL */
+  int32_t mode, G, r;
+  int32_t b, fl, hw, C;
+  int32_t dtype;
+  int32_t max_blocks; /* 0 = 2 per SM */
+  int32_t timeout_ms;
+} mimo_exchange_params;
+int mimo_exchange(const mimo_exchange_params* p, void* stream);
+/* Peer-shareable device memory for mimo_exchange: cudaMalloc'd, zero-filled, exported as a 64-byte CUDA IPC handle;
+ * mimo_peer_open maps another process's buffer into this process for the CURRENT device (peer access is enabled on
+ * first use). Bootstrap only (the handles travel over whatever the host uses, e.g. torch.distributed objects). */
+int mimo_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+int mimo_peer_open(const void* handle64, void** ptr);
+int mimo_peer_close(void* ptr);
+int mimo_peer_free(void* ptr);
 
 /* Elementwise / layout helpers (each one coalesced pass). */
 /* [b, c, f, h, w] (reference layout) -> [(b f), h, w, cpad] channels-last, zero-padding channels c..cpad */

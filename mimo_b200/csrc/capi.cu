@@ -101,6 +101,7 @@ extern "C" int mimo_abi_sizeof(int which) {
     case 3: return static_cast<int>(sizeof(mimo_groupnorm_params));
     case 4: return static_cast<int>(sizeof(mimo_attn_params));
     case 5: return static_cast<int>(sizeof(mimo_attn_temporal_params));
+    case 6: return static_cast<int>(sizeof(mimo_exchange_params));
   }
   return -1;
 }
@@ -117,4 +118,44 @@ extern "C" int mimo_device_check(int dev) {
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (major != 10) return mimo::set_error(MIMO_ERR_DEVICE, "device is not sm_100 (B200)");
   return MIMO_OK;
+}
+
+// ---- peer-shareable memory for mimo_exchange (bootstrap only) ----
+extern "C" int mimo_peer_alloc(int64_t bytes, void** ptr, void* handle64) {
+  if (!ptr || !handle64 || bytes <= 0) return mimo::set_error(MIMO_ERR_ARG, "mimo_peer_alloc: bad arguments");
+  if (int rc = mimo::ensure_device()) return rc;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, static_cast<size_t>(bytes));
+  if (e != cudaSuccess) return mimo::set_cuda_error("mimo_peer_alloc cudaMalloc", e);
+  e = cudaMemset(p, 0, static_cast<size_t>(bytes));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return mimo::set_cuda_error("mimo_peer_alloc", e);
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return MIMO_OK;
+}
+extern "C" int mimo_peer_open(const void* handle64, void** ptr) {
+  if (!ptr || !handle64) return mimo::set_error(MIMO_ERR_ARG, "mimo_peer_open: bad arguments");
+  if (int rc = mimo::ensure_device()) return rc;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return mimo::set_cuda_error("mimo_peer_open cudaIpcOpenMemHandle", e);
+  *ptr = p;
+  return MIMO_OK;
+}
+extern "C" int mimo_peer_close(void* ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  return e == cudaSuccess ? MIMO_OK : mimo::set_cuda_error("mimo_peer_close", e);
+}
+extern "C" int mimo_peer_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? MIMO_OK : mimo::set_cuda_error("mimo_peer_free", e);
 }

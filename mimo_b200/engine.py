@@ -237,7 +237,7 @@ class UNetEngine:
         if bank is not None:
             att = ops.attn_spatial(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], n, hw, self.spec.heads,
                                    bank_k=bank[:, :, :C], bank_v=bank[:, :, C:], bank_index=st["bank_index"],
-                                   n_bank_frames=(n // 2 if st["cfg"] else n))
+                                   n_bank_frames=st["n_bank_frames"])
         else:
             att = ops.attn_spatial(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], n, hw, self.spec.heads)
         hcur = ops.gemm(att, m["o1"][0], bias=m["o1"][1], residual=hcur, rowvec=st["xattn"][p],
@@ -246,36 +246,40 @@ class UNetEngine:
         return ops.gemm(hcur, m["pout"][0], bias=m["pout"][1], residual=x)
 
     def _motion(self, p, x, b, f, hw):
+        """VanillaTemporalModule (motion_module.py:77-91, 146-184, 238-261). Single GPU: f = all frames of the window.
+        Frame-sharded (self.xchg, G GPUs): this GPU holds f = F / G frames; the tokens are re-sharded to pixels for the
+        transformer block (every GPU then owns all F frames of hw / G pixels, so LN + PE, q/k/v, the attention over
+        frames, out-proj and the feed-forward are all local) and back, each by one peer-memory exchange kernel."""
         m = self.w[p]
         n = b * f
-        hcur = ops.groupnorm(x, *m["gn"], n, hw, groups=self.spec.motion_groups, eps=1e-6)
-        hcur = ops.gemm(hcur, m["pin"][0], bias=m["pin"][1])
-        C = hcur.shape[1]
-        rank, world, group = self.shard
-        if f * world > m["attn"][0]["pe"].shape[0]:
+        xg = self.xchg
+        G = xg.G if xg is not None else 1
+        F_ = f * G
+        if F_ > m["attn"][0]["pe"].shape[0]:
             # the reference fails here with a shape error (motion_module.py:277-279: x + pe[:, :x.size(1)])
-            raise L.MimoError(f"{f * world} frames in a window exceed temporal_position_encoding_max_len="
+            raise L.MimoError(f"{F_} frames in a window exceed temporal_position_encoding_max_len="
                               f"{m['attn'][0]['pe'].shape[0]}")
+        hcur = ops.groupnorm(x, *m["gn"], n, hw, groups=self.spec.motion_groups, eps=1e-6)
+        C = m["pin"][0].shape[0]
+        if G == 1:
+            hw_l = hw
+            hcur = ops.gemm(hcur, m["pin"][0], bias=m["pin"][1])
+        else:
+            if hw % G:
+                raise L.MimoError(f"{hw} tokens per frame cannot be split over a frame group of {G} GPUs")
+            hw_l = hw // G
+            ops.gemm(hcur, m["pin"][0], out=xg.bufs["A"].view(n * hw, C, x.dtype), bias=m["pin"][1])
+            hcur = xg.pull(0, "A", torch.empty((b * F_ * hw_l, C), dtype=x.dtype, device=x.device), b, f, hw, C)
         for a in m["attn"]:
-            if world == 1:
-                nh = ops.layernorm(hcur, *a["ln"], pe=a["pe"], rows_per_frame=hw, frames=f)
-                qkv = ops.gemm(nh, a["qkv"])
-                att = ops.attn_temporal(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], b, f, hw, self.spec.heads)
-            else:
-                # frames are sharded over `world` GPUs: this rank holds frames [rank*f, (rank+1)*f) of the window.
-                # Queries stay local; every rank's K|V block is all-gathered over NVLink (NCCL) and addressed in
-                # place as `world` chunks of f frames (no re-layout copy).
-                import torch.distributed as dist
-                nh = ops.layernorm(hcur, *a["ln"], pe=a["pe"], rows_per_frame=hw, frames=f, pe_frame_offset=rank * f)
-                q = ops.gemm(nh, a["qkv"][:C])
-                kv = ops.gemm(nh, a["qkv"][C:])
-                kv_all = torch.empty((world * kv.shape[0], 2 * C), dtype=kv.dtype, device=kv.device)
-                dist.all_gather_into_tensor(kv_all, kv, group=group)
-                att = ops.attn_temporal(q, kv_all[:, :C], kv_all[:, C:], b, f * world, hw, self.spec.heads, q_frames=f,
-                                        frames_per_chunk=f, chunk_stride_rows=kv.shape[0])
+            nh = ops.layernorm(hcur, *a["ln"], pe=a["pe"], rows_per_frame=hw_l, frames=F_)
+            qkv = ops.gemm(nh, a["qkv"])
+            att = ops.attn_temporal(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], b, F_, hw_l, self.spec.heads)
             hcur = ops.gemm(att, a["o"][0], bias=a["o"][1], residual=hcur)
         hcur = self._ff(hcur, m["ffn"], m["geglu"], m["ffo"])
-        return ops.gemm(hcur, m["pout"][0], bias=m["pout"][1], residual=x)
+        if G == 1:
+            return ops.gemm(hcur, m["pout"][0], bias=m["pout"][1], residual=x)
+        ops.gemm(hcur, m["pout"][0], out=xg.bufs["B"].view(b * F_ * hw_l, C, x.dtype), bias=m["pout"][1])
+        return xg.pull(1, "B", torch.empty_like(x), b, f, hw, C, residual=x)
 
     def _down(self, p, x, n, h, w):
         wp, b = self.w[p]
@@ -287,7 +291,7 @@ class UNetEngine:
         u = ops.upsample2x(x, n, h, w)
         return ops.conv3x3(u, wp, n, 2 * h, 2 * w, bias=b)
 
-    shard: tuple = (0, 1, None)  # (rank, world, process group) of the frame-sharded execution; world 1 = single GPU
+    xchg = None  # host.shard.Exchange of this GPU's frame group (None / G == 1: all frames of a window are local)
     taps: Optional[dict] = None  # debugging aid (scripts/gpu_probe.py): block outputs as [N, C, H, W] fp32 on CPU
 
     def _tap(self, name, x, n, h, w):
@@ -395,21 +399,30 @@ class UNetEngine:
         return new
 
     def set_cross_attn(self, ehs: torch.Tensor):
-        self.clip_state["xattn"] = self._store("xattn", self.cross_attn_vectors(ehs))
+        br = list(self.clip_state["branches"])
+        vec = {p: v[br].contiguous() for p, v in self.cross_attn_vectors(ehs).items()}  # this GPU's CFG branch(es)
+        self.clip_state["xattn"] = self._store("xattn", vec)
 
-    def begin_clip(self, ehs: torch.Tensor, banks: Dict[str, torch.Tensor], cfg: bool, frames: int):
-        """Per-clip state of the denoising UNet: folded cross-attention vectors, projected banks, bank routing."""
-        self.clip_state = {"banks": self._store("banks", banks), "cfg": cfg, "frames": 0, "batch": ehs.shape[0],
-                           "bank_index": None}
+    def begin_clip(self, ehs: torch.Tensor, banks: Dict[str, torch.Tensor], cfg: bool, frames: int,
+                   branches: Optional[Sequence[int]] = None):
+        """Per-clip state of the denoising UNet: folded cross-attention vectors, projected banks, bank routing.
+        `branches`: which rows of `ehs` (CFG branches: 0 = unconditional, 1 = conditional) this GPU evaluates; the
+        batch dimension of forward()'s sample is len(branches). Default: all of them."""
+        branches = tuple(range(ehs.shape[0])) if branches is None else tuple(branches)
+        self.clip_state = {"banks": self._store("banks", banks), "cfg": cfg, "frames": 0, "batch": len(branches),
+                           "branches": branches, "bank_index": None, "n_bank_frames": 0}
         self.set_cross_attn(ehs)
-        self.begin_clip_frames(frames, ehs.shape[0])
+        self.begin_clip_frames(frames, len(branches))
 
     def begin_clip_frames(self, frames: int, b: int):
         st = self.clip_state
-        idx = ([-1] * frames + [1] * frames) if st["cfg"] else [0] * (b * frames)
-        # unconditional rows ignore the bank (mutual_self_attention.py:177-197)
+        if b != len(st["branches"]):
+            raise L.MimoError(f"forward() got a batch of {b} but this engine evaluates branches {st['branches']}")
+        # unconditional rows ignore the bank (mutual_self_attention.py:177-197); conditional rows read bank 1
+        idx = sum(([-1 if br == 0 else 1] * frames for br in st["branches"]), []) if st["cfg"] else [0] * (b * frames)
         new = torch.tensor(idx, dtype=torch.int32, device=self.device)
-        st["bank_index"] = self._store(f"bank_index_{len(idx)}", {"i": new})["i"]
+        st["bank_index"] = self._store(f"bank_index_{len(idx)}_{st['branches']}", {"i": new})["i"]
+        st["n_bank_frames"] = sum(1 for i in idx if i >= 0)
         st["frames"] = frames
 
     def _forward_impl(self, sample: torch.Tensor, emb: torch.Tensor, pose_nhwc: Optional[torch.Tensor]) -> torch.Tensor:
@@ -441,7 +454,7 @@ class UNetEngine:
         t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep])
         emb = self._sinusoid(t.reshape(-1).expand(b) if t.numel() == 1 else t)
         sample = sample.contiguous()
-        if not self.use_graphs or self.taps is not None or ops.PROFILE is not None or self.shard[1] > 1:
+        if not self.use_graphs or self.taps is not None or ops.PROFILE is not None:
             return self._forward_impl(sample, emb, pose_nhwc)
         key = (tuple(sample.shape), sample.dtype, pose_nhwc is not None, st["bank_index"].data_ptr())
         g = self._graphs.get(key)

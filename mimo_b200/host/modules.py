@@ -346,7 +346,7 @@ class ReferenceAttentionControl:
         latents, ehs = pending
         den, ref = self.unet.engine(), writer.unet.engine()
         banks = ref.write_banks(latents, ehs, den)
-        den.begin_clip(ehs, banks, cfg=self.cfg, frames=1)
+        den.begin_clip(ehs, banks, cfg=self.cfg, frames=1, branches=getattr(self.unet, "_branches", None))
         self.unet._xattn_key = None
 
     def clear(self):

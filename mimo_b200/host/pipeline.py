@@ -102,14 +102,36 @@ class Pose2VideoPipeline:
         self.timings: Dict[str, float] = {}
         self.last_latents: Optional[torch.Tensor] = None
         self.io_bytes = {"h2d": 0, "d2h": 0}
-        self._shard = (0, 1, None)  # (rank, world, process group): frame-sharded execution over several GPUs
+        self._shard = (0, 1, None)  # (rank, world, process group): see enable_sharding()
 
-    def enable_frame_sharding(self, rank: int, world: int, group=None):
-        """Shard every context window's frames over `world` GPUs (one process per GPU, torch.distributed already
-        initialised). Per-frame work is local; the motion modules all-gather K/V over NVLink (engine._motion); the
-        per-window predictions, pose features and decoded frames are all-gathered so that every rank holds the
-        whole clip's latents (they are tiny) and the full result."""
+    def enable_sharding(self, rank: int, world: int, group=None, exchange_timeout_ms: int = 0):
+        """Partition every clip over `world` GPUs (one process per GPU, torch.distributed already initialised):
+        CFG branches x context windows x frames of a window, see host/shard.py. Per-frame work is local; each motion
+        module re-shards frames <-> pixels with a peer-memory exchange kernel (no NCCL on the data path); the
+        per-window predictions are all-gathered the same way once per step, so every rank holds the whole clip's
+        latents (tiny); pose features and decoded frames are computed sharded and gathered once per clip."""
         self._shard = (rank, world, group)
+        self._xchg_key, self._xchg_frame, self._xchg_world = None, None, None
+        self._xchg_timeout_ms = exchange_timeout_ms
+
+    enable_frame_sharding = enable_sharding  # round-1 name
+
+    def _exchanges(self, plan, nb: int, n_my_windows: int, fl: int, h: int, w: int, dtype):
+        """(frame-group exchange or None, world exchange): peer buffers sized for this geometry; collective."""
+        from .shard import Exchange
+        rank, world, group = self._shard
+        key = (plan, nb, n_my_windows, fl, h, w, dtype)
+        if getattr(self, "_xchg_key", None) != key:
+            esz = torch.empty((), dtype=dtype).element_size()
+            c0 = self.denoising_unet.config.block_out_channels[0]
+            tok = nb * fl * h * w * c0 * esz  # the widest token tensor of a forward: the first level's
+            kw = dict(timeout_ms=getattr(self, "_xchg_timeout_ms", 0))
+            self._xchg_frame = (Exchange.create(plan.frame_group(), rank, {"A": tok, "B": tok}, self.device, group, **kw)
+                                if plan.frame_ways > 1 else None)
+            self._xchg_world = Exchange.create(list(range(world)), rank, {"S": n_my_windows * nb * 4 * fl * h * w * esz},
+                                               self.device, group, **kw)
+            self._xchg_key = key
+        return self._xchg_frame, self._xchg_world
 
     # ------------------------------------------------------------------------------------------------
     def to(self, device=None, dtype=None):
@@ -241,6 +263,19 @@ class Pose2VideoPipeline:
             pose_fea = self.pose_guider.forward_nhwc(pose_px).reshape(F_, h * w, -1)  # channels-last, per frame
         mark("pose_guider")
 
+        context_scheduler = get_context_scheduler(context_schedule)
+        windows = list(context_scheduler(0, num_inference_steps, F_, context_frames, context_stride, context_overlap))
+        rep = 2 if do_cfg else 1
+        single = len(windows) == 1
+        plan = None
+        if world > 1:
+            from .shard import ShardPlan
+            if len({len(c) for c in windows}) != 1:
+                raise NotImplementedError("context windows of different lengths cannot be sharded")
+            plan = ShardPlan.make(world, rank, do_cfg, len(windows), len(windows[0]))
+        branches = plan.branches(do_cfg) if plan else tuple(range(rep))
+        nb = len(branches)
+
         # reference UNet once, banks -> denoising engine (pipeline :393-406, :480-490)
         writer = ReferenceAttentionControl(self.reference_unet, do_classifier_free_guidance=do_cfg, mode="write",
                                            batch_size=1, fusion_blocks="full")
@@ -248,42 +283,54 @@ class Pose2VideoPipeline:
                                            batch_size=1, fusion_blocks="full")
         self.reference_unet(ref_latents.to(dtype).repeat(2 if do_cfg else 1, 1, 1, 1), torch.zeros((), dtype=torch.int64),
                             encoder_hidden_states=ehs, return_dict=False)
+        self.denoising_unet._branches = branches  # the CFG branch(es) this GPU evaluates
         reader.update(writer)
         den = self.denoising_unet.engine()
-        den.shard = (rank, world, group)
         mark("reference_unet")
 
-        context_scheduler = get_context_scheduler(context_schedule)
-        windows = list(context_scheduler(0, num_inference_steps, F_, context_frames, context_stride, context_overlap))
-        rep = 2 if do_cfg else 1
-        single = len(windows) == 1
+        my_windows = plan.windows_of(len(windows)) if plan else list(range(len(windows)))
         win_inputs = []
-        for c in windows:  # the windows and their pose features are the same at every step (pipeline :493-500)
-            if world > 1:
-                if len(c) % world:
-                    raise NotImplementedError(f"a window of {len(c)} frames cannot be sharded over {world} GPUs")
-                fl = len(c) // world
-                cl = c[rank * fl:(rank + 1) * fl]  # this rank's frames of the window, in window order
-            else:
-                cl = c
-            pose_in = pose_fea[cl].reshape(1, len(cl) * h * w, -1).repeat(rep, 1, 1).reshape(rep * len(cl) * h * w, -1)
+        for wi in my_windows:  # the windows and their pose features are the same at every step (pipeline :493-500)
+            c = windows[wi]
+            cl = plan.local_frames(c) if plan else c  # this rank's frames of the window, in window order
+            pose_in = pose_fea[cl].reshape(1, len(cl) * h * w, -1).repeat(nb, 1, 1).reshape(nb * len(cl) * h * w, -1)
             win_inputs.append((c, cl, vid_bk[:, :, cl], pose_in.contiguous()))
+        if plan:
+            fl = len(win_inputs[0][1])
+            den.xchg, xw = self._exchanges(plan, nb, len(my_windows), fl, h, w, dtype)
+            stage = xw.bufs["S"].view(len(my_windows), nb * 4 * fl * h * w, dtype)
+            gathered = torch.empty((world, len(my_windows), nb, 4, fl, h, w), dtype=dtype, device=device)
+            gcols = next(c for c in (64, 32, 16, 8) if stage.numel() % c == 0)
+            from .shard import gather_layout
+            scatter = [(q, j, list(brs), torch.tensor(fr, dtype=torch.long, device=device))
+                       for q, j, brs, fr in gather_layout(plan, windows, do_cfg)]
+            counter_all = torch.zeros((F_,), device=device, dtype=dtype)
+            for c in windows:
+                counter_all[c] = counter_all[c] + 1
+        else:
+            den.xchg = None
         for i, t in enumerate(timesteps):
-            if not single:
+            if plan:
+                for j, (c, cl, bk_c, pose_in) in enumerate(win_inputs):
+                    lat_in = torch.cat([latents[:, :, cl], bk_c], dim=1).repeat(nb, 1, 1, 1, 1)
+                    stage[j].copy_(den.forward(lat_in, t, pose_in).reshape(-1))
+                xw.pull(2, "S", gathered.view(-1, gcols), 1, 1, stage.numel() // gcols, gcols)
                 noise_pred = torch.zeros((rep, 4, F_, h, w), device=device, dtype=dtype)
-                counter = torch.zeros((F_,), device=device, dtype=dtype)
-            for c, cl, bk_c, pose_in in win_inputs:
-                lat_in = torch.cat([latents[:, :, cl], bk_c], dim=1).repeat(rep, 1, 1, 1, 1)
-                pred = den.forward(lat_in, t, pose_in)
-                if world > 1:  # [rep, 4, f/world, h, w] per rank -> the window's full prediction on every rank
-                    parts = torch.empty((world * pred.shape[0],) + tuple(pred.shape[1:]), dtype=pred.dtype, device=device)
-                    dist.all_gather_into_tensor(parts, pred.contiguous(), group=group)  # concatenated along dim 0
-                    pred = parts.view((world,) + tuple(pred.shape)).permute(1, 2, 0, 3, 4, 5).reshape(rep, 4, len(c), h, w)
-                if single:
-                    noise_pred, counter = pred, None
-                else:
-                    noise_pred[:, :, c] = noise_pred[:, :, c] + pred  # :540-542
-                    counter[c] = counter[c] + 1
+                for q, j, brs, fidx in scatter:
+                    noise_pred[brs[0]:brs[-1] + 1] = noise_pred[brs[0]:brs[-1] + 1].index_add(2, fidx, gathered[q, j])
+                counter = None if single else counter_all
+            else:
+                if not single:
+                    noise_pred = torch.zeros((rep, 4, F_, h, w), device=device, dtype=dtype)
+                    counter = torch.zeros((F_,), device=device, dtype=dtype)
+                for c, cl, bk_c, pose_in in win_inputs:
+                    lat_in = torch.cat([latents[:, :, cl], bk_c], dim=1).repeat(rep, 1, 1, 1, 1)
+                    pred = den.forward(lat_in, t, pose_in)
+                    if single:
+                        noise_pred, counter = pred, None
+                    else:
+                        noise_pred[:, :, c] = noise_pred[:, :, c] + pred  # :540-542
+                        counter[c] = counter[c] + 1
             co = self.scheduler.step_coefficients(t)
             if do_cfg:
                 ops.cfg_ddim_step(noise_pred[0], noise_pred[1], latents, guidance_scale, *co, counter=counter,

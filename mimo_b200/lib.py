@@ -97,6 +97,19 @@ class AttnTemporalParams(C.Structure):
     ]
 
 
+MAX_PEERS = 8
+
+
+class ExchangeParams(C.Structure):
+    _fields_ = [
+        ("peer_src", C.c_void_p * MAX_PEERS), ("peer_ready", C.c_void_p * MAX_PEERS),
+        ("ctl", C.c_void_p), ("dst", C.c_void_p), ("residual", C.c_void_p),
+        ("mode", C.c_int32), ("G", C.c_int32), ("r", C.c_int32),
+        ("b", C.c_int32), ("fl", C.c_int32), ("hw", C.c_int32), ("C", C.c_int32),
+        ("dtype", C.c_int32), ("max_blocks", C.c_int32), ("timeout_ms", C.c_int32),
+    ]
+
+
 # every symbol include/mimo_b200.h declares: name -> (restype, argtypes)
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SYMBOLS = {
@@ -113,6 +126,11 @@ SYMBOLS = {
     "mimo_layernorm": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _F, _VP, _I64, _I32, _I32, _I32, _VP]),
     "mimo_attn_spatial": (C.c_int, [C.POINTER(AttnParams), _VP]),
     "mimo_attn_temporal": (C.c_int, [C.POINTER(AttnTemporalParams), _VP]),
+    "mimo_exchange": (C.c_int, [C.POINTER(ExchangeParams), _VP]),
+    "mimo_peer_alloc": (C.c_int, [_I64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "mimo_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mimo_peer_close": (C.c_int, [_VP]),
+    "mimo_peer_free": (C.c_int, [_VP]),
     "mimo_ncfhw_to_nhwc": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "mimo_nhwc_to_ncfhw": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "mimo_upsample2x": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
@@ -144,7 +162,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
         fn.restype = res
         fn.argtypes = args
-    for which, st in enumerate((Epilogue, GemmParams, Conv3x3Params, GroupNormParams, AttnParams, AttnTemporalParams)):
+    for which, st in enumerate((Epilogue, GemmParams, Conv3x3Params, GroupNormParams, AttnParams, AttnTemporalParams,
+                             ExchangeParams)):
         if lib.mimo_abi_sizeof(which) != C.sizeof(st):
             raise MimoError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes in lib.py but "
                             f"{lib.mimo_abi_sizeof(which)} in {LIB_PATH.name}; rebuild the library")

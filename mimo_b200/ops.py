@@ -255,6 +255,31 @@ def attn_temporal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int,
     return out
 
 
+def exchange(xg, mode: int, name: str, dst: torch.Tensor, b: int, fl: int, hw: int, Cdim: int,
+             residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One mimo_exchange of frame group `xg` (host/shard.py: Exchange): pull from every member's source buffer `name`
+    into the local tensor `dst` (mode 0 frames->pixels, 1 pixels->frames (+ residual), 2 all-gather)."""
+    assert dst.is_contiguous() and (residual is None or (residual.is_contiguous() and residual.shape == dst.shape))
+    p = L.ExchangeParams()
+    src, flags = xg.bufs[name], xg.flags
+    for s in range(xg.G):
+        p.peer_src[s] = src.peer_ptrs[s]
+        p.peer_ready[s] = flags.peer_ptrs[s]
+    p.ctl, p.dst, p.residual = _ptr(xg.ctl), _ptr(dst), _ptr(residual)
+    p.mode, p.G, p.r = int(mode), xg.G, xg.r
+    p.b, p.fl, p.hw, p.C = int(b), int(fl), int(hw), int(Cdim)
+    p.dtype = _dt(dst)
+    p.max_blocks, p.timeout_ms = int(xg.max_blocks), int(xg.timeout_ms)
+    rows = b * fl * hw * (xg.G if mode == 2 else 1)
+    need = (b * fl * hw if mode != 1 else b * fl * hw) * Cdim * dst.element_size()
+    if need > src.nbytes or dst.numel() != rows * Cdim:
+        raise L.MimoError(f"exchange: source buffer '{name}' ({src.nbytes} B) or dst ({tuple(dst.shape)}) does not fit "
+                          f"b={b} fl={fl} hw={hw} C={Cdim} mode={mode}")
+    with _Call("exchange", 1, 0.0, 2.0 * dst.numel() * dst.element_size() + (dst.numel() * dst.element_size() if residual is not None else 0)):
+        L.check(L.load().mimo_exchange(C.byref(p), _stream()), "mimo_exchange")
+    return dst
+
+
 def ncfhw_to_nhwc(src: torch.Tensor, cpad: int, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     b, c, f, h, w = src.shape
     assert src.is_contiguous() and src.dtype in (torch.float32, dtype)
