@@ -372,6 +372,16 @@ class AutoencoderKL(_EngineModel):
         self._materialise(schema.vae_schema(block_out_channels, layers_per_block, latent_channels, in_channels,
                                             out_channels))
 
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, **unused):
+        """diffusers layout: <path>/config.json + diffusion_pytorch_model.{safetensors,bin} (run_animate.py:70-72)."""
+        p, cfg = _UNetBase._config_from_dir(path, subfolder)
+        keys = ("block_out_channels", "layers_per_block", "latent_channels", "in_channels", "out_channels",
+                "norm_num_groups", "scaling_factor")
+        model = cls(**{k: cfg[k] for k in keys if k in cfg})
+        model.load_state_dict(_UNetBase._load_weights_file(p), strict=True)
+        return model
+
     def engine(self):
         self._require_cuda()
         if self._engine is None or self._engine_key != self._key():
