@@ -101,6 +101,13 @@ typedef struct {
   mimo_epilogue ep;
 } mimo_conv3x3_params;
 int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream);
+/* Upsample3D (src/models/resnet.py:53-90): nearest x2 (H, W) followed by the 3x3 / pad 1 conv, WITHOUT materialising
+ * the upsampled tensor. x0 is the [n, h, w, c0] source, out the [n, 2h, 2w, cout] result (row stride ldo). Output pixel
+ * (2y+a, 2x+b) only sees source rows {y-1+a, y+a} and columns {x-1+b, x+b}: four 2x2-tap implicit-GEMM convolutions (one
+ * per parity class) whose weights are the sums of the 3x3 taps that land on the same source pixel - 4/9 of the FLOPs.
+ * w: [4 classes (2a+b)][cout, 4 * c0], K index = (2*iy + ix) * c0 + channel, packed by the host
+ * (mimo_b200.ops.pack_conv_up2x_weight). Epilogue: bias / scale / SiLU only. */
+int mimo_conv_up2x(const mimo_conv3x3_params* p, void* stream);
 
 /* im2col gather for the convolutions the TMA path does not cover (stride 2, nearest-x2 upsampled input):
  * col[(n,oy,ox), tap*c + ch] = x[n, (oy*stride-1+ky) >> up, (ox*stride-1+kx) >> up, ch], zero outside.
@@ -109,9 +116,9 @@ int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream);
 int mimo_im2col3x3(const void* x, void* col, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride,
                    int32_t upshift, int32_t pad_lo, int64_t ldcol, int32_t dtype, void* stream);
 
-/* GroupNorm over channels-last activations, optional SiLU, optional two-source virtual concat: ONE pass over HBM
- * (each image slab stays in registers between the statistics and the normalisation) and deterministic (fixed-order
- * reductions, no floating-point atomics). stats: workspace of mimo_groupnorm_workspace_bytes(p) bytes, 16-byte aligned,
+/* GroupNorm over channels-last activations, optional SiLU, optional two-source virtual concat. Deterministic: a
+ * statistics pass publishes per-slab partial sums, the normalisation pass adds them in a fixed order (no floating-point
+ * atomics; bit-identical run to run). stats: workspace of mimo_groupnorm_workspace_bytes(p) bytes, 16-byte aligned,
  * contents irrelevant. Replaces InflatedGroupNorm / nn.GroupNorm + F.silu
  * (src/models/resnet.py:20-28, 220-221, 231, 237; transformer_3d.py:58-60,124; motion_module.py:119-121,156). */
 typedef struct {

@@ -25,4 +25,9 @@ struct AttnArgs {
 int launch_attn_pp(bool bf16, const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& bk,
                    const CUtensorMap& bv, const AttnArgs& a, int n, cudaStream_t st);
 
+// two softmax threads per query row, row sum by the tensor pipe (attn_spatial_pp2.cu); d + 1 <= 128
+bool attn_pp2_supports(int d);
+int launch_attn_pp2(bool bf16, const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& bk,
+                    const CUtensorMap& bv, const AttnArgs& a, int n, cudaStream_t st);
+
 }  // namespace mimo

@@ -63,6 +63,8 @@ struct ConvGeom {
   int kb0, kb1;     // 64-wide K blocks (per tap in conv mode) of source 0 / 1
   int a_bytes;      // bytes one A box deposits in shared memory
   int chunk_bytes;  // bytes one output / residual box moves (TW*TH*TN rows x 64 B)
+  int ntaps;        // 9 (3x3) or 4 (one parity class of nearest-x2 upsample + 3x3, see mimo_conv_up2x)
+  signed char tdx[9], tdy[9];  // input offset of tap t relative to the output pixel
 };
 
 template <int BN, bool kRes>
@@ -164,7 +166,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int n_tile = tile % num_n_tiles;
       int x0, y0, n0;
       tile_origin(m_tile, x0, y0, n0);
-      int rem = 0, dx = -1, dy = -1, tap_k = 0;  // conv: k-block inside the tap, tap offsets, tap * ctot
+      int rem = 0, tap = 0, dx = g.tdx[0], dy = g.tdy[0], tap_k = 0;  // conv: k-block inside the tap, tap offsets, tap * ctot
       for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (ep.trace && blockIdx.x == 0 && lane == 0 && it < 512) ep.trace[2560 + it] = clock64();
@@ -197,10 +199,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         if (++rem == kb_per_tap) {
           rem = 0;
           tap_k += g.ctot;
-          if (++dx == 2) {
-            dx = -1;
-            ++dy;
-          }
+          if (++tap == g.ntaps) tap = 0;
+          dx = g.tdx[tap];
+          dy = g.tdy[tap];
         }
         if (++stage == Cfg::kStages) {
           stage = 0;
@@ -731,17 +732,12 @@ extern "C" int mimo_gemm(const mimo_gemm_params* p, void* stream) {
   return launch_bn<false>(bn, res, m, p->M, p->N, mt, nt, nkb, g, ep, st);
 }
 
-extern "C" int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream) {
-  if (!p || !p->x0 || !p->w || !p->out) return set_error(MIMO_ERR_ARG, "mimo_conv3x3: null pointer");
-  if (p->n <= 0 || p->h <= 0 || p->w_ <= 0 || p->cout <= 0 || p->c0 <= 0)
-    return set_error(MIMO_ERR_ARG, "mimo_conv3x3: empty problem");
+// One implicit-GEMM convolution launch: `ntaps` taps at offsets (tdx, tdy) over the [n, h, w, c] input(s); the output
+// (and residual) pixel (n, y, x) lives at out + ((n * oh + y * sy) * ow + x * sx) * ldo elements, i.e. a strided view of a
+// larger image when (sx, sy) != (1, 1).
+static int conv_launch(const mimo_conv3x3_params* p, const void* w, int ntaps, const signed char* tdx,
+                       const signed char* tdy, void* out, int sx, int sy, int ow, int oh, void* stream) {
   const int c1 = p->x1 ? p->c1 : 0;
-  if ((p->c0 % 8) || (c1 % 8) || (p->cout % 8) || (p->ldo % 8))
-    return set_error(MIMO_ERR_ARG, "mimo_conv3x3: channel counts must be multiples of 8");
-  if (p->ep.act == MIMO_ACT_GEGLU) return set_error(MIMO_ERR_ARG, "mimo_conv3x3: GEGLU not supported");
-  if (p->ep.residual && (p->ep.ld_res % 8)) return set_error(MIMO_ERR_ARG, "mimo_conv3x3: ld_res % 8 != 0");
-  if (int rc = ensure_device()) return rc;
-
   ConvGeom g = {};
   g.conv = 1;
   g.H = p->h;
@@ -764,42 +760,91 @@ extern "C" int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream) {
   g.kb1 = (c1 + BK - 1) / BK;
   g.a_bytes = g.TW * g.TH * g.TN * BK * 2;
   g.chunk_bytes = g.TW * g.TH * g.TN * 64;
+  g.ntaps = ntaps;
+  for (int t = 0; t < 9; ++t) {
+    g.tdx[t] = t < ntaps ? tdx[t] : 0;
+    g.tdy[t] = t < ntaps ? tdy[t] : 0;
+  }
   const int mt = g.tiles_w * g.tiles_h * tiles_n;
   const int bn = pick_bn(p->cout, false, mt);
   const int nt = (p->cout + bn - 1) / bn;
-  const int nkb = 9 * (g.kb0 + g.kb1);
+  const int nkb = ntaps * (g.kb0 + g.kb1);
   const long long Mrows = static_cast<long long>(p->n) * p->h * p->w_;
-  if (Mrows > 0x7fffffffLL) return set_error(MIMO_ERR_ARG, "mimo_conv3x3: too many pixels");
+  if (Mrows > 0x7fffffffLL) return set_error(MIMO_ERR_ARG, "mimo_conv: too many pixels");
   const bool res = p->ep.residual != nullptr;
 
   Maps m;
-  auto nhwc_map = [&](CUtensorMap* tm, const void* base, int c, long long pitch, uint32_t box_c, int swz) {
+  auto nhwc_map = [&](CUtensorMap* tm, const void* base, int c, long long pitch, uint32_t box_c, int swz, int px,
+                      int py, int iw, int ih) {
+    // pixel (n, y, x) at base + ((n * ih + y * py) * iw + x * px) * pitch elements
     const uint64_t dim[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(p->w_), static_cast<uint64_t>(p->h),
                              static_cast<uint64_t>(p->n)};
-    const uint64_t str[3] = {static_cast<uint64_t>(pitch) * 2, static_cast<uint64_t>(p->w_) * pitch * 2,
-                             static_cast<uint64_t>(p->h) * p->w_ * pitch * 2};
+    const uint64_t str[3] = {static_cast<uint64_t>(px) * pitch * 2, static_cast<uint64_t>(py) * iw * pitch * 2,
+                             static_cast<uint64_t>(ih) * iw * pitch * 2};
     const uint32_t box[4] = {box_c, static_cast<uint32_t>(g.TW), static_cast<uint32_t>(g.TH),
                              static_cast<uint32_t>(g.TN)};
     return encode_tmap(tm, p->dtype, 4, base, dim, str, box, swz);
   };
-  if (int rc = nhwc_map(&m.a0, p->x0, p->c0, p->c0, BK, 128)) return rc;
+  if (int rc = nhwc_map(&m.a0, p->x0, p->c0, p->c0, BK, 128, 1, 1, p->w_, p->h)) return rc;
   m.a1 = m.a0;
   if (c1)
-    if (int rc = nhwc_map(&m.a1, p->x1, c1, c1, BK, 128)) return rc;
+    if (int rc = nhwc_map(&m.a1, p->x1, c1, c1, BK, 128, 1, 1, p->w_, p->h)) return rc;
   {
-    const uint64_t dim[2] = {static_cast<uint64_t>(9) * g.ctot, static_cast<uint64_t>(p->cout)};
-    const uint64_t str[1] = {static_cast<uint64_t>(9) * g.ctot * 2};
+    const uint64_t dim[2] = {static_cast<uint64_t>(ntaps) * g.ctot, static_cast<uint64_t>(p->cout)};
+    const uint64_t str[1] = {static_cast<uint64_t>(ntaps) * g.ctot * 2};
     const uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
-    if (int rc = encode_tmap(&m.b, p->dtype, 2, p->w, dim, str, box)) return rc;
+    if (int rc = encode_tmap(&m.b, p->dtype, 2, w, dim, str, box)) return rc;
   }
-  if (int rc = nhwc_map(&m.out, p->out, p->cout, p->ldo, 32, 64)) return rc;
+  if (int rc = nhwc_map(&m.out, out, p->cout, p->ldo, 32, 64, sx, sy, ow, oh)) return rc;
   m.res = m.out;
   if (res)
-    if (int rc = nhwc_map(&m.res, p->ep.residual, p->cout, p->ep.ld_res, 32, 64)) return rc;
+    if (int rc = nhwc_map(&m.res, p->ep.residual, p->cout, p->ep.ld_res, 32, 64, 1, 1, p->w_, p->h)) return rc;
 
   EpiArgs ep = make_epi(p->ep, p->cout);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dtype == MIMO_BF16)
     return launch_bn<true>(bn, res, m, static_cast<int>(Mrows), p->cout, mt, nt, nkb, g, ep, st);
   return launch_bn<false>(bn, res, m, static_cast<int>(Mrows), p->cout, mt, nt, nkb, g, ep, st);
+}
+
+static int conv_check(const mimo_conv3x3_params* p, const char* who) {
+  if (!p || !p->x0 || !p->w || !p->out) return set_error(MIMO_ERR_ARG, "mimo_conv: null pointer");
+  if (p->n <= 0 || p->h <= 0 || p->w_ <= 0 || p->cout <= 0 || p->c0 <= 0)
+    return set_error(MIMO_ERR_ARG, "mimo_conv: empty problem");
+  const int c1 = p->x1 ? p->c1 : 0;
+  if ((p->c0 % 8) || (c1 % 8) || (p->cout % 8) || (p->ldo % 8))
+    return set_error(MIMO_ERR_ARG, "mimo_conv: channel counts must be multiples of 8");
+  if (p->ep.act == MIMO_ACT_GEGLU) return set_error(MIMO_ERR_ARG, "mimo_conv: GEGLU not supported");
+  if (p->ep.residual && (p->ep.ld_res % 8)) return set_error(MIMO_ERR_ARG, "mimo_conv: ld_res % 8 != 0");
+  (void)who;
+  return ensure_device();
+}
+
+extern "C" int mimo_conv3x3(const mimo_conv3x3_params* p, void* stream) {
+  if (int rc = conv_check(p, "mimo_conv3x3")) return rc;
+  static const signed char dx[9] = {-1, 0, 1, -1, 0, 1, -1, 0, 1};
+  static const signed char dy[9] = {-1, -1, -1, 0, 0, 0, 1, 1, 1};
+  return conv_launch(p, p->w, 9, dx, dy, p->out, 1, 1, p->w_, p->h, stream);
+}
+
+// nearest-x2 upsampling followed by a 3x3 / pad 1 convolution, without the upsampled tensor: output pixel (2y+a, 2x+b)
+// only ever sees the 2x2 source neighbourhood {y-1+a, y+a} x {x-1+b, x+b}, so each of the four parity classes (a, b) is a
+// 2x2-tap convolution over the SOURCE image whose weights are sums of the 3x3 taps that land on the same source pixel
+// (packed by the host: w = [4 classes][cout, 4 * cin], class = 2a + b, tap = 2 iy + ix). 4/9 of the FLOPs, no 4x buffer.
+extern "C" int mimo_conv_up2x(const mimo_conv3x3_params* p, void* stream) {
+  if (int rc = conv_check(p, "mimo_conv_up2x")) return rc;
+  if (p->ep.residual || p->ep.rowvec) return set_error(MIMO_ERR_ARG, "mimo_conv_up2x: bias / activation epilogue only");
+  const int ctot = p->c0 + (p->x1 ? p->c1 : 0);
+  const size_t esz = 2;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const signed char dx[4] = {static_cast<signed char>(b - 1), static_cast<signed char>(b),
+                                 static_cast<signed char>(b - 1), static_cast<signed char>(b)};
+      const signed char dy[4] = {static_cast<signed char>(a - 1), static_cast<signed char>(a - 1),
+                                 static_cast<signed char>(a), static_cast<signed char>(a)};
+      const char* w = static_cast<const char*>(p->w) + static_cast<size_t>(2 * a + b) * p->cout * 4 * ctot * esz;
+      char* out = static_cast<char*>(p->out) + (static_cast<size_t>(a) * 2 * p->w_ + b) * p->ldo * esz;
+      if (int rc = conv_launch(p, w, 4, dx, dy, out, 2, 2, 2 * p->w_, 2 * p->h, stream)) return rc;
+    }
+  return MIMO_OK;
 }

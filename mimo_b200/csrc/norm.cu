@@ -10,16 +10,13 @@
 namespace mimo {
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm(+SiLU): ONE pass over HBM (one read, one write), deterministic.
-//
-// A work item is a slab of P*ITERS pixels x all C channels of one image; the slab stays in REGISTERS between the
-// statistics phase and the normalise phase. Per item: load slab -> per-(slab, group) partial (sum, sumsq), reduced
-// inside the block in a fixed order -> published to part[image][slab][group] -> arrive on the image's counter ->
-// wait until all slabs of the image have arrived -> every block sums the image's partials in the same fixed order
-// (bit-identical run to run and block to block; no floating-point atomics anywhere) -> normalise, affine, SiLU, store.
-// Blocks walk the items image-major (item = block + k * grid), so the slabs of one image are in flight together; the
-// launch is cooperative (all blocks co-resident), which makes the per-image wait deadlock-free: the lowest
-// unfinished image only ever waits on blocks whose earlier items are complete.
+// GroupNorm(+SiLU), deterministic: two streaming kernels, no floating-point atomics.
+//   pass 1: every block reduces its slab of pixels to per-group (sum, sumsq) in a FIXED order (registers -> shared
+//           memory -> one thread per group) and publishes them: part[image][slab][group][2]
+//   pass 2: every block sums the slabs' partials of its image in the same fixed order (bit-identical statistics in
+//           every block and run to run), then normalises + affine (+ SiLU) with 128-bit loads / stores.
+// (A one-pass variant that kept the slab in registers across a per-image arrival barrier was measured at 1.5 TB/s on
+// the 64x64 level - the barrier serialises the blocks of an image - against 2.2 TB/s for these two full-width passes.)
 // ------------------------------------------------------------------------------------------------
 struct GnArgs {
   const void* x0;
@@ -27,13 +24,12 @@ struct GnArgs {
   const void* gamma;
   const void* beta;
   void* out;
-  float* part;        // [n][bpi][groups][2] = (sum, sumsq) per slab
-  unsigned* arrived;  // [n] slabs of the image whose partials are published (zeroed by the launcher)
+  float* part;  // [n][bpi][groups][2] = (sum, sumsq) per slab
   int c0, c1, C, hw, groups, cpg;
   int vecs;  // C / 8
   int P;     // pixels processed side by side by one block
-  int bpi;   // slabs (work items) per image
-  int n;
+  int pix_per_block;
+  int bpi;   // slabs per image
   float eps;
   int silu;
 };
@@ -50,12 +46,12 @@ __device__ __forceinline__ uint4 gn_load(const GnArgs& a, long long pix, int cv)
 
 constexpr int kGnMaxThreads = 320;
 
-template <bool kBf16, int ITERS>
-__global__ void __launch_bounds__(kGnMaxThreads, ITERS >= 16 ? 1 : 2) gn_onepass_kernel(GnArgs a) {
+// pass 1: per-(image, slab, group) sum and sum of squares
+template <bool kBf16>
+__global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(GnArgs a) {
   using C = Cvt<kBf16>;
   __shared__ float4 s_red[kGnMaxThreads];  // per-thread (sumA, sqA, sumB, sqB)
-  __shared__ float s_tot[4][128];          // up to 4 partial sums of (group, {sum, sumsq})
-  __shared__ float s_mean[64], s_rstd[64];
+  const int n = blockIdx.y;
   const int tid = threadIdx.x;
   const int cv = tid % a.vecs;
   const int pl = tid / a.vecs;
@@ -64,36 +60,15 @@ __global__ void __launch_bounds__(kGnMaxThreads, ITERS >= 16 ? 1 : 2) gn_onepass
   const int gA = ch0 / a.cpg;
   int split = (gA + 1) * a.cpg - ch0;  // channels [0, split) of this vector belong to gA, the rest to gA + 1
   if (split > 8) split = 8;
-  const int ppb = a.P * ITERS;
-  const float inv_cnt = 1.0f / (static_cast<float>(a.hw) * a.cpg);
-  // gamma / beta of this thread's 8 channels, packed (unpacked on use: 8 registers instead of 16)
-  uint32_t wg[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
+  float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
   if (active) {
-    const uint4 ug = *reinterpret_cast<const uint4*>(static_cast<const typename C::T*>(a.gamma) + ch0);
-    const uint4 ub = *reinterpret_cast<const uint4*>(static_cast<const typename C::T*>(a.beta) + ch0);
-    wg[0] = ug.x, wg[1] = ug.y, wg[2] = ug.z, wg[3] = ug.w;
-    wb[0] = ub.x, wb[1] = ub.y, wb[2] = ub.z, wb[3] = ub.w;
-  }
-  const int g2 = a.groups * 2;
-  const int total = a.n * a.bpi;
-#pragma unroll 1
-  for (int item = blockIdx.x; item < total; item += gridDim.x) {
-    const int n = item / a.bpi;
-    const int pb = item - n * a.bpi;
-    const int p0 = pb * ppb + pl;
-    const long long pix0 = static_cast<long long>(n) * a.hw;
-    // ---- load the slab (all loads in flight before the first use) ----
-    uint4 u[ITERS];
-#pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const int p = p0 + i * a.P;
-      u[i] = (active && p < a.hw) ? gn_load<kBf16>(a, pix0 + p, cv) : make_uint4(0, 0, 0, 0);
-    }
-    // ---- partial statistics of the slab ----
-    float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
-#pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+    const int p_begin = blockIdx.x * a.pix_per_block;
+    int p_end = p_begin + a.pix_per_block;
+    if (p_end > a.hw) p_end = a.hw;
+#pragma unroll 4
+    for (int p = p_begin + pl; p < p_end; p += a.P) {
+      const uint4 u = gn_load<kBf16>(a, static_cast<long long>(n) * a.hw + p, cv);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 t = C::unpack(w[j]);
@@ -101,147 +76,134 @@ __global__ void __launch_bounds__(kGnMaxThreads, ITERS >= 16 ? 1 : 2) gn_onepass
         if (2 * j + 1 < split) sA += t.y, qA += t.y * t.y; else sB += t.y, qB += t.y * t.y;
       }
     }
-    s_red[tid] = make_float4(sA, qA, sB, qB);
-    __syncthreads();
-    for (int g = tid; g < a.groups; g += blockDim.x) {  // fixed order: vectors touching group g, then pixel lanes
-      const int v_lo = (g * a.cpg) >> 3;
-      const int v_hi = ((g + 1) * a.cpg - 1) >> 3;
-      float s = 0.f, q = 0.f;
-      for (int v = v_lo; v <= v_hi; ++v) {
-        const bool as_a = (v * 8) / a.cpg == g;  // this vector's first group is g (else g is its second group)
-        for (int l = 0; l < a.P; ++l) {
-          const float4 r = s_red[l * a.vecs + v];
-          s += as_a ? r.x : r.z;
-          q += as_a ? r.y : r.w;
-        }
-      }
-      float* dst = a.part + (static_cast<long long>(item) * a.groups + g) * 2;
-      __stcg(dst, s);
-      __stcg(dst + 1, q);
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();  // release: everything the block published (ordered before the barrier) precedes the arrival
-      atomicAdd(a.arrived + n, 1u);
-      unsigned seen;
-      unsigned spins = 0;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.arrived + n) : "memory");
-        if (seen >= static_cast<unsigned>(a.bpi)) break;
-        __nanosleep(40);
-        if (++spins > (1u << 24)) {  // seconds: a scheduling bug must trap, never hang the GPU
-          printf("mimo: groupnorm image barrier timeout (block %d image %d: %u of %d)\n", blockIdx.x, n, seen, a.bpi);
-          __trap();
-        }
-      } while (true);
-    }
-    __syncthreads();
-    // ---- image totals: the same fixed order in every block -> bit-identical statistics everywhere ----
-    {
-      const int parts = a.bpi >= 16 ? 4 : 1;  // a function of the shape only: the summation order never varies
-      const float* src = a.part + static_cast<long long>(n) * a.bpi * g2;
-      for (int idx = tid; idx < parts * g2; idx += blockDim.x) {
-        const int k = idx % g2, part = idx / g2;
-        float acc = 0.f;
-        for (int b = part; b < a.bpi; b += parts) acc += __ldcg(src + static_cast<long long>(b) * g2 + k);
-        s_tot[part][k] = acc;
-      }
-      __syncthreads();
-      for (int g = tid; g < a.groups; g += blockDim.x) {
-        float s = 0.f, q = 0.f;
-        for (int part = 0; part < parts; ++part) {
-          s += s_tot[part][2 * g];
-          q += s_tot[part][2 * g + 1];
-        }
-        const float mean = s * inv_cnt;
-        float var = q * inv_cnt - mean * mean;
-        var = var < 0.f ? 0.f : var;
-        s_mean[g] = mean;
-        s_rstd[g] = rsqrtf(var + a.eps);
-      }
-      __syncthreads();
-    }
-    // ---- normalise + affine (+ SiLU) from registers, store ----
-    if (active) {
-      const float mA = s_mean[gA], rA = s_rstd[gA];
-      const float mB = split < 8 ? s_mean[gA + 1] : 0.f, rB = split < 8 ? s_rstd[gA + 1] : 0.f;
-      float sc[8], sh[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 gg = C::unpack(wg[j]);
-        const float2 bb = C::unpack(wb[j]);
-        const float m0 = 2 * j < split ? mA : mB, r0 = 2 * j < split ? rA : rB;
-        const float m1 = 2 * j + 1 < split ? mA : mB, r1 = 2 * j + 1 < split ? rA : rB;
-        sc[2 * j] = r0 * gg.x;
-        sh[2 * j] = bb.x - m0 * r0 * gg.x;
-        sc[2 * j + 1] = r1 * gg.y;
-        sh[2 * j + 1] = bb.y - m1 * r1 * gg.y;
-      }
-#pragma unroll
-      for (int i = 0; i < ITERS; ++i) {
-        const int p = p0 + i * a.P;
-        if (p < a.hw) {
-          const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 t = C::unpack(w[j]);
-            f[2 * j] = fmaf(t.x, sc[2 * j], sh[2 * j]);
-            f[2 * j + 1] = fmaf(t.y, sc[2 * j + 1], sh[2 * j + 1]);
-          }
-          if (a.silu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
-          }
-          uint4 o;
-          o.x = C::pack(f[0], f[1]);
-          o.y = C::pack(f[2], f[3]);
-          o.z = C::pack(f[4], f[5]);
-          o.w = C::pack(f[6], f[7]);
-          *reinterpret_cast<uint4*>(static_cast<typename C::T*>(a.out) + (pix0 + p) * a.C + ch0) = o;
-        }
+  }
+  s_red[tid] = make_float4(sA, qA, sB, qB);
+  __syncthreads();
+  for (int g = tid; g < a.groups; g += blockDim.x) {  // fixed order: vectors touching group g, then pixel lanes
+    const int v_lo = (g * a.cpg) >> 3;
+    const int v_hi = ((g + 1) * a.cpg - 1) >> 3;
+    float s = 0.f, q = 0.f;
+    for (int v = v_lo; v <= v_hi; ++v) {
+      const bool as_a = (v * 8) / a.cpg == g;  // this vector's first group is g (else g is its second group)
+      for (int l = 0; l < a.P; ++l) {
+        const float4 r = s_red[l * a.vecs + v];
+        s += as_a ? r.x : r.z;
+        q += as_a ? r.y : r.w;
       }
     }
-    __syncthreads();  // s_red / s_tot / s_mean are reused by the next item
+    float* dst = a.part + ((static_cast<long long>(n) * a.bpi + blockIdx.x) * a.groups + g) * 2;
+    dst[0] = s;
+    dst[1] = q;
   }
 }
 
-static int g_gn_max_iters = 8;  // 8: two 40 KB slabs per SM in different phases; 16 (test hook): one 80 KB slab
+// pass 2: image statistics from the slab partials (fixed order), then normalise + affine (+ SiLU)
+template <bool kBf16>
+__global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(GnArgs a) {
+  using C = Cvt<kBf16>;
+  __shared__ float s_tot[4][128];
+  __shared__ float s_mean[64], s_rstd[64];
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int g2 = a.groups * 2;
+  {
+    const int parts = a.bpi >= 16 ? 4 : 1;  // a function of the shape only: the summation order never varies
+    const float* src = a.part + static_cast<long long>(n) * a.bpi * g2;
+    for (int idx = tid; idx < parts * g2; idx += blockDim.x) {
+      const int k = idx % g2, part = idx / g2;
+      float acc = 0.f;
+      for (int b = part; b < a.bpi; b += parts) acc += src[static_cast<long long>(b) * g2 + k];
+      s_tot[part][k] = acc;
+    }
+    __syncthreads();
+    const float inv_cnt = 1.0f / (static_cast<float>(a.hw) * a.cpg);
+    for (int g = tid; g < a.groups; g += blockDim.x) {
+      float s = 0.f, q = 0.f;
+      for (int part = 0; part < parts; ++part) {
+        s += s_tot[part][2 * g];
+        q += s_tot[part][2 * g + 1];
+      }
+      const float mean = s * inv_cnt;
+      float var = q * inv_cnt - mean * mean;
+      var = var < 0.f ? 0.f : var;
+      s_mean[g] = mean;
+      s_rstd[g] = rsqrtf(var + a.eps);
+    }
+    __syncthreads();
+  }
+  const int cv = tid % a.vecs;
+  const int pl = tid / a.vecs;
+  if (pl >= a.P) return;
+  const int ch0 = cv * 8;
+  const int gA = ch0 / a.cpg;
+  int split = (gA + 1) * a.cpg - ch0;
+  if (split > 8) split = 8;
+  float sc[8], sh[8];
+  {
+    const uint4 ug = *reinterpret_cast<const uint4*>(static_cast<const typename C::T*>(a.gamma) + ch0);
+    const uint4 ub = *reinterpret_cast<const uint4*>(static_cast<const typename C::T*>(a.beta) + ch0);
+    const uint32_t wg[4] = {ug.x, ug.y, ug.z, ug.w};
+    const uint32_t wb[4] = {ub.x, ub.y, ub.z, ub.w};
+    const float mA = s_mean[gA], rA = s_rstd[gA];
+    const float mB = split < 8 ? s_mean[gA + 1] : 0.f, rB = split < 8 ? s_rstd[gA + 1] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 gg = C::unpack(wg[j]);
+      const float2 bb = C::unpack(wb[j]);
+      const float m0 = 2 * j < split ? mA : mB, r0 = 2 * j < split ? rA : rB;
+      const float m1 = 2 * j + 1 < split ? mA : mB, r1 = 2 * j + 1 < split ? rA : rB;
+      sc[2 * j] = r0 * gg.x;
+      sh[2 * j] = bb.x - m0 * r0 * gg.x;
+      sc[2 * j + 1] = r1 * gg.y;
+      sh[2 * j + 1] = bb.y - m1 * r1 * gg.y;
+    }
+  }
+  const int p_begin = blockIdx.x * a.pix_per_block;
+  int p_end = p_begin + a.pix_per_block;
+  if (p_end > a.hw) p_end = a.hw;
+#pragma unroll 4
+  for (int p = p_begin + pl; p < p_end; p += a.P) {
+    const long long pix = static_cast<long long>(n) * a.hw + p;
+    const uint4 u = gn_load<kBf16>(a, pix, cv);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = C::unpack(w[j]);
+      f[2 * j] = fmaf(t.x, sc[2 * j], sh[2 * j]);
+      f[2 * j + 1] = fmaf(t.y, sc[2 * j + 1], sh[2 * j + 1]);
+    }
+    if (a.silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+    }
+    uint4 o;
+    o.x = C::pack(f[0], f[1]);
+    o.y = C::pack(f[2], f[3]);
+    o.z = C::pack(f[4], f[5]);
+    o.w = C::pack(f[6], f[7]);
+    *reinterpret_cast<uint4*>(static_cast<typename C::T*>(a.out) + pix * a.C + ch0) = o;
+  }
+}
+
 // launch geometry shared by mimo_groupnorm and mimo_groupnorm_workspace_bytes
 struct GnPlan {
-  int vecs, P, iters, bpi, threads;
+  int vecs, P, pix_per_block, bpi, threads;
 };
 static GnPlan gn_plan(int n, int hw, int C) {
   GnPlan pl;
   pl.vecs = C / 8;
-  pl.P = kGnMaxThreads / pl.vecs;
+  pl.P = 256 / pl.vecs;
   if (pl.P < 1) pl.P = 1;
   if (pl.P > hw) pl.P = hw;
   pl.threads = ((pl.vecs * pl.P + 31) / 32) * 32;
-  int iters = g_gn_max_iters;
-  const long long want = 2LL * num_sms();  // enough slabs to fill the machine twice, if the tensor allows it
-  while (iters > 1 && (pl.P * (iters >> 1) >= hw || static_cast<long long>(n) * div_up(hw, pl.P * iters) < want)) iters >>= 1;
-  pl.iters = iters;
-  pl.bpi = static_cast<int>(div_up(hw, pl.P * iters));
+  int iters = 16;
+  // large images: more pixels per block keep the partial table (re-read by every block of pass 2) at <= 128 slabs
+  while (static_cast<long long>(hw) > 128LL * pl.P * iters && iters < 4096) iters *= 2;
+  pl.pix_per_block = pl.P * iters;
+  pl.bpi = static_cast<int>(div_up(hw, pl.pix_per_block));
+  (void)n;
   return pl;
-}
-
-template <bool kBf16, int ITERS>
-static cudaError_t gn_launch(const GnArgs& a, int threads, cudaStream_t st) {
-  static int occ = 0;  // per (dtype, ITERS) instantiation; the block size only ever shrinks below kGnMaxThreads
-  if (!occ) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_onepass_kernel<kBf16, ITERS>, kGnMaxThreads, 0);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) occ = 1;
-  }
-  const long long items = static_cast<long long>(a.n) * a.bpi;
-  long long grid = static_cast<long long>(occ) * num_sms();
-  if (grid > items) grid = items;
-  GnArgs args = a;
-  void* kargs[] = {&args};
-  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(gn_onepass_kernel<kBf16, ITERS>),
-                                     dim3(static_cast<unsigned>(grid)), dim3(threads), kargs, 0, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,17 +430,11 @@ static int gn_check(const mimo_groupnorm_params* p, int* Cout) {
   return MIMO_OK;
 }
 
-extern "C" int mimo_debug_gn_max_iters(int iters) {
-  if (iters == 16 || iters == 8 || iters == 4 || iters == 2 || iters == 1) g_gn_max_iters = iters;
-  return g_gn_max_iters;
-}
-
 extern "C" int64_t mimo_groupnorm_workspace_bytes(const mimo_groupnorm_params* p) {
   int C = 0;
   if (int rc = gn_check(p, &C)) return rc;
   const GnPlan pl = gn_plan(p->n, p->hw, C);
-  // per-slab partials + one arrival counter per image (rounded up to 16 bytes)
-  return static_cast<int64_t>(p->n) * pl.bpi * p->groups * 2 * sizeof(float) + ((static_cast<int64_t>(p->n) * 4 + 15) / 16) * 16;
+  return static_cast<int64_t>(p->n) * pl.bpi * p->groups * 2 * sizeof(float);
 }
 
 extern "C" int mimo_groupnorm(const mimo_groupnorm_params* p, void* stream) {
@@ -495,7 +451,6 @@ extern "C" int mimo_groupnorm(const mimo_groupnorm_params* p, void* stream) {
   a.beta = p->beta;
   a.out = p->out;
   a.part = p->stats;
-  a.arrived = reinterpret_cast<unsigned*>(p->stats + static_cast<int64_t>(p->n) * pl.bpi * p->groups * 2);
   a.c0 = p->c0;
   a.c1 = p->x1 ? p->c1 : 0;
   a.C = C;
@@ -504,21 +459,20 @@ extern "C" int mimo_groupnorm(const mimo_groupnorm_params* p, void* stream) {
   a.cpg = C / p->groups;
   a.vecs = pl.vecs;
   a.P = pl.P;
+  a.pix_per_block = pl.pix_per_block;
   a.bpi = pl.bpi;
-  a.n = p->n;
   a.eps = p->eps;
   a.silu = p->silu;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(a.arrived, 0, sizeof(unsigned) * p->n, st);
-  if (e != cudaSuccess) return set_cuda_error("groupnorm memset", e);
-  const bool bf = p->dtype == MIMO_BF16;
-  switch (pl.iters) {
-    case 16: e = bf ? gn_launch<true, 16>(a, pl.threads, st) : gn_launch<false, 16>(a, pl.threads, st); break;
-    case 8: e = bf ? gn_launch<true, 8>(a, pl.threads, st) : gn_launch<false, 8>(a, pl.threads, st); break;
-    case 4: e = bf ? gn_launch<true, 4>(a, pl.threads, st) : gn_launch<false, 4>(a, pl.threads, st); break;
-    case 2: e = bf ? gn_launch<true, 2>(a, pl.threads, st) : gn_launch<false, 2>(a, pl.threads, st); break;
-    default: e = bf ? gn_launch<true, 1>(a, pl.threads, st) : gn_launch<false, 1>(a, pl.threads, st); break;
+  dim3 grid(pl.bpi, p->n);
+  if (p->dtype == MIMO_BF16) {
+    gn_stats_kernel<true><<<grid, pl.threads, 0, st>>>(a);
+    gn_apply_kernel<true><<<grid, pl.threads, 0, st>>>(a);
+  } else {
+    gn_stats_kernel<false><<<grid, pl.threads, 0, st>>>(a);
+    gn_apply_kernel<false><<<grid, pl.threads, 0, st>>>(a);
   }
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("groupnorm launch", e);
   return MIMO_OK;
 }

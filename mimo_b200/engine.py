@@ -84,6 +84,10 @@ class _Packer:
         w, b = self.lin(p)
         return ops.pack_geglu_weight(w, b)
 
+    def conv_up(self, p):
+        """the 3x3 conv behind a nearest-x2 upsampling, as four 2x2-tap parity classes (ops.pack_conv_up2x_weight)"""
+        return ops.pack_conv_up2x_weight(self.t(p + ".weight")), self.t(p + ".bias")
+
 
 class UNetEngine:
     """Executes the denoising UNet3D (motion=True) or the reference UNet2D bank pass (motion=False)."""
@@ -164,7 +168,7 @@ class UNetEngine:
                 if spec.motion:
                     add_mm(f"up_blocks.{i}.motion_modules.{j}")
             if i < nb - 1:
-                W[f"up_blocks.{i}.up"] = pk.conv3(f"up_blocks.{i}.upsamplers.0.conv")
+                W[f"up_blocks.{i}.up"] = pk.conv_up(f"up_blocks.{i}.upsamplers.0.conv")
         if spec.out_head:
             W["norm_out"] = pk.norm("conv_norm_out")
             W["conv_out"] = pk.conv3("conv_out")
@@ -288,8 +292,7 @@ class UNetEngine:
 
     def _up(self, p, x, n, h, w):
         wp, b = self.w[p]
-        u = ops.upsample2x(x, n, h, w)
-        return ops.conv3x3(u, wp, n, 2 * h, 2 * w, bias=b)
+        return ops.conv_up2x(x, wp, n, h, w, bias=b)  # Upsample3D (resnet.py:53-90) without the 4x tensor
 
     xchg = None  # host.shard.Exchange of this GPU's frame group (None / G == 1: all frames of a window are local)
     taps: Optional[dict] = None  # debugging aid (scripts/gpu_probe.py): block outputs as [N, C, H, W] fp32 on CPU
@@ -624,7 +627,7 @@ class VAEDecoderEngine(_VAEBlocks):
             for j in range(self.n_res):
                 self._add_res(pk, f"decoder.up_blocks.{i}.resnets.{j}")
             if pk.has(f"decoder.up_blocks.{i}.upsamplers.0.conv.weight"):
-                W[f"up{i}"] = pk.conv3(f"decoder.up_blocks.{i}.upsamplers.0.conv")
+                W[f"up{i}"] = pk.conv_up(f"decoder.up_blocks.{i}.upsamplers.0.conv")
         W["norm_out"] = pk.norm("decoder.conv_norm_out")
         W["conv_out"] = pk.conv3("decoder.conv_out")
         self.out_channels = sd["decoder.conv_out.weight"].shape[0]
@@ -642,9 +645,8 @@ class VAEDecoderEngine(_VAEBlocks):
             for j in range(self.n_res):
                 x = self._res(f"decoder.up_blocks.{i}.resnets.{j}", x, n, h, w)
             if f"up{i}" in self.w:
-                u = ops.upsample2x(x, n, h, w)
+                x = ops.conv_up2x(x, self.w[f"up{i}"][0], n, h, w, bias=self.w[f"up{i}"][1])
                 h, w = 2 * h, 2 * w
-                x = ops.conv3x3(u, self.w[f"up{i}"][0], n, h, w, bias=self.w[f"up{i}"][1])
         x = ops.groupnorm(x, *self.w["norm_out"], n, h * w, groups=self.groups, eps=1e-6, silu=True)
         y = ops.conv3x3(x, self.w["conv_out"][0], n, h, w, bias=self.w["conv_out"][1])
         out = ops.nhwc_to_ncfhw(y, n, self.out_channels, 1, h, w)  # [n, 3, 1, H, W]

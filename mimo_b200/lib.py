@@ -120,6 +120,7 @@ SYMBOLS = {
     "mimo_gemm": (C.c_int, [C.POINTER(GemmParams), _VP]),
     "mimo_gemm_geglu_granule": (C.c_int, [_I32]),
     "mimo_conv3x3": (C.c_int, [C.POINTER(Conv3x3Params), _VP]),
+    "mimo_conv_up2x": (C.c_int, [C.POINTER(Conv3x3Params), _VP]),
     "mimo_im2col3x3": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I64, _I32, _VP]),
     "mimo_groupnorm": (C.c_int, [C.POINTER(GroupNormParams), _VP]),
     "mimo_groupnorm_workspace_bytes": (C.c_int64, [C.POINTER(GroupNormParams)]),
@@ -140,7 +141,7 @@ SYMBOLS = {
     "mimo_cfg_ddim_step": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _I64, _F, _F, _F, _F, _F, _I32, _VP]),
 }
 # test hook, not part of the public header
-_DEBUG_SYMBOLS = {"mimo_debug_gn_max_iters": (C.c_int, [C.c_int]), "mimo_debug_force_bn": (C.c_int, [C.c_int]), "mimo_debug_attn_variant": (C.c_int, [C.c_int]),
+_DEBUG_SYMBOLS = {"mimo_debug_force_bn": (C.c_int, [C.c_int]), "mimo_debug_attn_variant": (C.c_int, [C.c_int]),
                   "mimo_debug_attn_trace": (C.c_int, [C.c_void_p]),
                   "mimo_debug_gemm_trace": (C.c_int, [C.c_void_p])}
 

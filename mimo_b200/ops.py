@@ -138,6 +138,29 @@ def conv3x3(x0: torch.Tensor, w: torch.Tensor, n: int, h: int, wd: int, out: Opt
     return out
 
 
+def conv_up2x(x: torch.Tensor, w4: torch.Tensor, n: int, h: int, wd: int, *, bias=None, scale=1.0, act=L.ACT_NONE,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nearest-x2 upsample + 3x3 conv of channels-last x [n*h*wd, c] -> [n*2h*2wd, cout]; w4 from pack_conv_up2x_weight."""
+    c = x.shape[1]
+    cout = w4.shape[1]
+    assert x.is_contiguous() and w4.is_contiguous() and w4.shape == (4, cout, 4 * c) and x.shape[0] == n * h * wd
+    if out is None:
+        out = torch.empty((n * 4 * h * wd, cout), dtype=x.dtype, device=x.device)
+    p = L.Conv3x3Params()
+    p.x0, p.c0 = _ptr(x), c
+    p.x1, p.c1 = None, 0
+    p.w = _ptr(w4)
+    p.out, p.ldo = _ptr(out), out.stride(0)
+    p.n, p.h, p.w_, p.cout = n, h, wd, cout
+    p.dtype = _dt(x)
+    p.ep = _epilogue(bias, None, 1, None, scale, act)
+    M = n * h * wd
+    # algorithmic work of the REFERENCE op (9 taps on the 4x image); the kernel executes 4/9 of it
+    with _Call("conv3x3", 4, 2.0 * 4 * M * cout * 9 * c, 2.0 * (M * c + 16 * c * cout + 4 * M * cout)):
+        L.check(L.load().mimo_conv_up2x(C.byref(p), _stream()), "mimo_conv_up2x")
+    return out
+
+
 def im2col3x3(x: torch.Tensor, n: int, h: int, wd: int, *, stride=1, upshift=0, pad_lo=1,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     c = x.shape[1]
@@ -175,7 +198,7 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int,
         stats = torch.empty(((need + 3) // 4,), dtype=torch.float32, device=x0.device)
     assert x0.is_contiguous() and out.is_contiguous() and stats.numel() * 4 >= need
     p.stats = _ptr(stats)
-    with _Call("groupnorm", 1, 0.0, 2.0 * 2 * out.numel()):  # algorithmic: one read + one write
+    with _Call("groupnorm", 2, 0.0, 2.0 * 2 * out.numel()):  # algorithmic: one read + one write
         L.check(L.load().mimo_groupnorm(C.byref(p), _stream()), "mimo_groupnorm")
     return out
 
@@ -360,6 +383,24 @@ def pack_conv3x3_weight(w: torch.Tensor, cin_pad: Optional[int] = None, cout_pad
     p = torch.zeros((cout_pad, 9, cin_pad), dtype=w.dtype, device=w.device)
     p[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
     return p.reshape(cout_pad, 9 * cin_pad).contiguous()
+
+
+def pack_conv_up2x_weight(w: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """OIHW [cout, cin, 3, 3] of the conv that FOLLOWS a nearest-x2 upsampling -> [4, cout_pad, 4 * cin_pad] for
+    mimo_conv_up2x: class 2a+b holds, for tap (iy, ix), the sum (in fp32, rounded once) of the 3x3 taps (ky, kx) that read
+    source pixel (y - 1 + a + iy, x - 1 + b + ix) when producing output pixel (2y + a, 2x + b)."""
+    cout, cin = w.shape[:2]
+    cin_pad, cout_pad = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
+    sets = {0: ([0], [1, 2]), 1: ([0, 1], [2])}  # parity -> (taps landing on the first / second source row)
+    wf = w.float()
+    out = torch.zeros((4, cout_pad, 4, cin_pad), dtype=torch.float32, device=w.device)
+    for a in range(2):
+        for bb in range(2):
+            for iy in range(2):
+                for ix in range(2):
+                    acc = sum(wf[:, :, ky, kx] for ky in sets[a][iy] for kx in sets[bb][ix])
+                    out[2 * a + bb, :cout, 2 * iy + ix, :cin] = acc
+    return out.reshape(4, cout_pad, 4 * cin_pad).to(w.dtype).contiguous()
 
 
 def pack_geglu_weight(w: torch.Tensor, b: Optional[torch.Tensor]):

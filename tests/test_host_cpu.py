@@ -145,3 +145,27 @@ def test_weight_packers_lay_out_what_the_kernels_index():
         tile, off = divmod(j, g)
         assert torch.equal(wp[tile * 2 * g + off], wg[j]) and torch.equal(wp[tile * 2 * g + g + off], wg[inner + j])
         assert bp[tile * 2 * g + off] == b[j] and bp[tile * 2 * g + g + off] == b[inner + j]
+
+
+def test_conv_up2x_weight_packing_equals_interpolate_plus_conv():
+    """The parity-class weights of mimo_conv_up2x (ops.pack_conv_up2x_weight) restate nearest-x2 + 3x3 conv exactly:
+    evaluated with torch on the CPU against F.interpolate + conv2d (src/models/resnet.py:70-90)."""
+    import torch.nn.functional as F
+
+    from mimo_b200 import ops
+    torch.manual_seed(0)
+    cin, cout, n, h, w = 8, 16, 2, 5, 7
+    W = torch.randn(cout, cin, 3, 3)
+    x = torch.randn(n, cin, h, w)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), W, padding=1)
+    w4 = ops.pack_conv_up2x_weight(W).reshape(4, cout, 4, cin)
+    out = torch.zeros(n, cout, 2 * h, 2 * w)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for a in range(2):
+        for b in range(2):
+            for iy in range(2):
+                for ix in range(2):
+                    dy, dx = a - 1 + iy, b - 1 + ix  # the offsets csrc/gemm_tcgen05.cu: mimo_conv_up2x uses
+                    src = xp[:, :, 1 + dy:1 + dy + h, 1 + dx:1 + dx + w]
+                    out[:, :, a::2, b::2] += torch.einsum("oc,nchw->nohw", w4[2 * a + b, :, 2 * iy + ix], src)
+    assert float((out - ref).abs().max()) < 1e-4

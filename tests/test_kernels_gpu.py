@@ -68,3 +68,26 @@ def test_cfg_ddim_step_matches_torch_fp16_expression():
         assert want.dtype == torch.float16
         diff = (got.float() - want.float()).abs().max()
         assert float(diff) <= 2e-3, (t, float(diff))
+
+
+def test_conv_up2x_matches_interpolate_plus_conv(probe):
+    """Upsample3D (resnet.py:53-90) as four parity-class 2x2-tap convolutions over the source image vs
+    F.interpolate(nearest) + conv2d in fp32; UNet and VAE-decoder shapes, ragged widths, SiLU epilogue."""
+    import torch.nn.functional as F
+
+    from mimo_b200 import lib as L
+    from mimo_b200 import ops
+    for n, h, w, cin, cout, act in [(3, 8, 8, 1280, 1280, L.ACT_NONE), (2, 32, 32, 640, 640, L.ACT_NONE),
+                                    (1, 64, 64, 512, 512, L.ACT_NONE), (2, 5, 7, 64, 72, L.ACT_SILU),
+                                    (1, 130, 3, 16, 8, L.ACT_NONE)]:
+        torch.manual_seed(n * 100 + h)
+        W = (torch.randn(cout, cin, 3, 3, device="cuda") / (3 * cin ** 0.5)).half()
+        b = torch.randn(cout, device="cuda").half()
+        x = torch.randn(n, cin, h, w, device="cuda").half()
+        ref = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), W.float(), b.float(), padding=1)
+        if act == L.ACT_SILU:
+            ref = F.silu(ref)
+        xr = x.permute(0, 2, 3, 1).reshape(n * h * w, cin).contiguous()
+        got = ops.conv_up2x(xr, ops.pack_conv_up2x_weight(W), n, h, w, bias=b, act=act)
+        got = got.reshape(n, 2 * h, 2 * w, -1)[..., :cout].permute(0, 3, 1, 2)
+        assert probe.report(f"conv_up2x n={n} {h}x{w} {cin}->{cout}", got, ref, tol=2e-3)
