@@ -49,6 +49,29 @@ TFLOP_PER_FRAME = 49.3
 CONFIG = {"workload": "512x512 x 24-frame animate, 20 DDIM steps, CFG 3.5, fp16 (BASELINE.json configs[1])",
           "frames": FRAMES, "ddim_steps": DDIM_STEPS, "guidance_scale": GUIDANCE,
           "l2": "inputs/weights per forward >> 126 MB L2; no explicit flush"}
+DTYPE, DTYPE_NAME, NOISE_BK = torch.float16, "fp16", False
+
+
+def select_config(k: int) -> None:
+    """BASELINE.json configs[k-1]. 2 (default, also 3 = the same clip on 8 GPUs): the metric's configuration. 4 and 5 are
+    extra lines for the 8-GPU node: `bench.py --config 4|5` (TFLOP per output frame from SURVEY.md §8d)."""
+    global WIDTH, HEIGHT, FRAMES, DDIM_STEPS, METRIC, TFLOP_PER_FRAME, CONFIG, DTYPE, DTYPE_NAME, NOISE_BK
+    if k in (2, 3):
+        return
+    if k == 4:
+        WIDTH = HEIGHT = 768
+        FRAMES, DDIM_STEPS, TFLOP_PER_FRAME = 48, 30, 285.7
+        DTYPE, DTYPE_NAME = torch.bfloat16, "bf16"
+        name = "768x768 x 48-frame animate (3 context windows), 30 DDIM steps, CFG 3.5, bf16 (BASELINE.json configs[3])"
+    elif k == 5:
+        FRAMES, DDIM_STEPS, TFLOP_PER_FRAME, NOISE_BK = 64, 20, 72.0, True
+        name = ("512x512 x 64-frame character edit (4 context windows, a distinct background per frame), 20 DDIM steps, "
+                "CFG 3.5, fp16 (BASELINE.json configs[4]); scene compositing is host-side in run_edit.py and not timed")
+    else:
+        raise SystemExit(f"--config {k}: BASELINE.json has configs 1..5 (1 is the CPU plumbing case: tests/)")
+    METRIC = f"frames/sec @ {WIDTH}x{HEIGHT}x{FRAMES}f, {DDIM_STEPS} DDIM steps"
+    CONFIG = {"workload": name, "frames": FRAMES, "ddim_steps": DDIM_STEPS, "guidance_scale": GUIDANCE,
+              "l2": "inputs/weights per forward >> 126 MB L2; no explicit flush"}
 
 SCHED_KW = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, steps_offset=1,
                 prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")
@@ -56,7 +79,7 @@ MOTION_KW = dict(num_attention_heads=8, num_transformer_block=1, attention_block
                  temporal_position_encoding=True, temporal_position_encoding_max_len=32, temporal_attention_dim_div=1)
 
 
-def synthetic_inputs(frames: int, size: int, seed: int = 0):
+def synthetic_inputs(frames: int, size: int, seed: int = 0, noise_bk: bool = False):
     """seeded uint8 reference image, pose frames = black with a coloured blob, white backgrounds."""
     import PIL.Image
     rng = np.random.RandomState(seed)
@@ -66,7 +89,8 @@ def synthetic_inputs(frames: int, size: int, seed: int = 0):
         a = np.zeros((size, size, 3), np.uint8)
         a[size // 4 + i: size // 2 + i, size // 3: size // 3 + size // 8] = rng.randint(11, 256, 3)
         poses.append(PIL.Image.fromarray(a))
-        bks.append(PIL.Image.fromarray(np.full((size, size, 3), 255, np.uint8)))
+        bks.append(PIL.Image.fromarray(rng.randint(0, 256, (size, size, 3), dtype=np.uint8) if noise_bk
+                                       else np.full((size, size, 3), 255, np.uint8)))
     return ref_img, poses, bks
 
 
@@ -135,7 +159,7 @@ def build_pipeline(device, rank: int = 0, world: int = 1):
                                                           projection_dim=768)).eval()
     pipe = Pose2VideoPipeline(vae=vae, image_encoder=clip, reference_unet=ref, denoising_unet=den, pose_guider=pg,
                               scheduler=DDIMScheduler(**SCHED_KW))
-    pipe.to(device, dtype=torch.float16)
+    pipe.to(device, dtype=DTYPE)
     if world > 1:
         pipe.enable_frame_sharding(rank, world)
     return pipe
@@ -153,7 +177,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     pipe = build_pipeline(device, rank, world)
-    ref_img, poses, bks = synthetic_inputs(FRAMES, WIDTH)
+    ref_img, poses, bks = synthetic_inputs(FRAMES, WIDTH, noise_bk=NOISE_BK)
 
     def sync():
         if world > 1:
@@ -164,7 +188,7 @@ def run_ours(args):
         return torch.Generator().manual_seed(42 + i)
 
     # ---- device-resident runs (value) ------------------------------------------------------------------
-    host = pipe.preprocess(ref_img, poses, bks, WIDTH, HEIGHT, FRAMES, clip_seed(0), torch.float16)
+    host = pipe.preprocess(ref_img, poses, bks, WIDTH, HEIGHT, FRAMES, clip_seed(0), DTYPE)
     dev_in = {k: v.to(device) for k, v in host.items()}
     if args.one_clip:
         t0 = time.perf_counter()
@@ -175,7 +199,7 @@ def run_ours(args):
         return
     # one noise tensor per step, drawn like prepare_latents does (CPU generator, fp16) and resident before timing
     lat_shape = tuple(host["latents"].shape)
-    seeds = [torch.randn(lat_shape, generator=clip_seed(1000 + i), dtype=torch.float16).to(device)
+    seeds = [torch.randn(lat_shape, generator=clip_seed(1000 + i), dtype=DTYPE).to(device)
              for i in range(args.steps)]
     for i in range(args.warmup):
         pipe.sample_tensors(dev_in, DDIM_STEPS, GUIDANCE)
@@ -318,13 +342,15 @@ def run_ours(args):
     par = "1 GPU"
     if world > 1:
         from mimo_b200.host.shard import ShardPlan
-        pl = ShardPlan.make(world, 0, True, 1, FRAMES)
+        from mimo_b200.host.context import uniform
+        wins = list(uniform(0, DDIM_STEPS, FRAMES, 24, 1, 4))
+        pl = ShardPlan.make(world, 0, True, len(wins), len(wins[0]))
         par = (f"{world} GPUs = CFG branches x{pl.cfg_ways} * windows x{pl.win_ways} * frames x{pl.frame_ways}; "
                "frames<->pixels exchange over NVLink peer memory (mimo_exchange), no NCCL on the data path")
     line = {
         "metric": METRIC, "value": round(value, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "fp16", "data": "synthetic", "config": dict(CONFIG), "parallelism": par,
+        "vs_baseline": None, "dtype": DTYPE_NAME, "data": "synthetic", "config": dict(CONFIG), "parallelism": par,
         "e2e": {"value": round(FRAMES / e2e_s, 4), "unit": "frames/s", "h2d_bytes_per_step": pipe.io_bytes["h2d"],
                 "d2h_bytes_per_step": pipe.io_bytes["d2h"], "clips_timed": k_e2e},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -496,11 +522,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config number: 2 (default, the metric), 4, 5")
     ap.add_argument("--dump-calls", default=None, help="write every profiled C-ABI call (name, flops, bytes, ms) as CSV")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU sample (development runs)")
     ap.add_argument("--one-clip", action="store_true",
                     help="run exactly one device-resident clip and exit (for `ncu` launch lists; not a bench value)")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         run_reference(args)
         return

@@ -248,6 +248,17 @@ int mimo_add(const void* a, const void* b, void* out, int64_t count, int32_t dty
 /* out = silu(x) */
 int mimo_silu(const void* x, void* out, int64_t count, int32_t dtype, void* stream);
 
+/* out = x * sigmoid(1.702 x): CLIP's quick_gelu (transformers CLIPMLP [3P]; the image encoder of pipeline :378-385) */
+int mimo_quick_gelu(const void* x, void* out, int64_t count, int32_t dtype, void* stream);
+
+/* Scene compositing of run_edit.py:282-300, one frame, one pass (all images uint8 [H, W, 3] on the device):
+ *   res = canvas * mask + bk * (1 - mask);  [res = res * (1 - occ/255) + vid * (occ/255)];  [out = prev * (1 - factor)
+ *   + res * factor];  out -> uint8 by truncation. mask: float32 [H, W] feather mask placed on the full frame; occ: uint8
+ *   [H, W] or NULL (then vid is NULL too); prev: the frame composited from the previous, overlapping clip or NULL.
+ * Intermediate types follow numpy's promotion in the reference, so the bytes are identical. */
+int mimo_composite_frame(const void* canvas, const void* bk, const float* mask, const void* occ, const void* vid,
+                         const void* prev, double factor, void* out, int64_t pixels, void* stream);
+
 /* Classifier-free guidance + DDIM (v-prediction, eta = 0) update, one pass:
  *   eps = (pred_u + g * (pred_c - pred_u)) / counter ; x0 = sa_t * x - s1a_t * v ; e = sa_t * v + s1a_t * x ;
  *   x_prev = sa_p * x0 + s1a_p * e.   latents/pred_* are [count]; math in fp32, stored in `dtype`.

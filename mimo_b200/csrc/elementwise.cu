@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(void* __restrict__ xp
   }
 }
 
-template <bool kBf16, int kOp>  // 0: add, 1: silu
+template <bool kBf16, int kOp>  // 0: add, 1: silu, 2: quick-GELU x * sigmoid(1.702 x) (CLIP's hidden_act)
 __global__ void ew_kernel(const void* __restrict__ a, const void* __restrict__ b, void* __restrict__ out,
                           long long nvec) {
   using C = Cvt<kBf16>;
@@ -185,8 +185,10 @@ __global__ void ew_kernel(const void* __restrict__ a, const void* __restrict__ b
       if (kOp == 0) {
         const float2 y = C::unpack(wb[j]);
         o[j] = C::pack(x.x + y.x, x.y + y.y);
-      } else {
+      } else if (kOp == 1) {
         o[j] = C::pack(silu_f(x.x), silu_f(x.y));
+      } else {
+        o[j] = C::pack(__fdividef(x.x, 1.0f + __expf(-1.702f * x.x)), __fdividef(x.y, 1.0f + __expf(-1.702f * x.y)));
       }
     }
     static_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -357,6 +359,19 @@ extern "C" int mimo_silu(const void* x, void* out, int64_t count, int32_t dtype,
   else
     ew_kernel<false, 1><<<ew_grid(nvec, 256), 256, 0, st>>>(x, nullptr, out, nvec);
   MIMO_CHECK_LAUNCH("silu launch");
+  return MIMO_OK;
+}
+
+extern "C" int mimo_quick_gelu(const void* x, void* out, int64_t count, int32_t dtype, void* stream) {
+  if (!x || !out || count <= 0 || (count % 8)) return set_error(MIMO_ERR_ARG, "mimo_quick_gelu: bad arguments");
+  if (int rc = ensure_device()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long nvec = count / 8;
+  if (dtype == MIMO_BF16)
+    ew_kernel<true, 2><<<ew_grid(nvec, 256), 256, 0, st>>>(x, nullptr, out, nvec);
+  else
+    ew_kernel<false, 2><<<ew_grid(nvec, 256), 256, 0, st>>>(x, nullptr, out, nvec);
+  MIMO_CHECK_LAUNCH("quick_gelu launch");
   return MIMO_OK;
 }
 

@@ -95,6 +95,31 @@ class UNetEngine:
     def __init__(self, sd: SD, spec: UNetSpec, device, dtype=torch.float16):
         L.check(L.load().mimo_device_check(torch.device(device).index or 0), "mimo_device_check")
         self.spec, self.device, self.dtype = spec, torch.device(device), dtype
+        self.clip_state: Optional[dict] = None
+        self._persist: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._graphs: Dict[tuple, dict] = {}
+        self.use_graphs = True
+        self._launches_per_forward = 0
+        # packed weights: from the on-disk cache when MIMO_B200_WEIGHT_CACHE is set and holds this state dict
+        from .host import weight_cache as WC
+        cache = WC.cache_dir()
+        cfile = None
+        if cache is not None:
+            key = WC.fingerprint(sd, f"unet|{spec}|{dtype}|{L.load().mimo_version().decode()}")
+            cfile = cache / f"unet-{key}.safetensors"
+            if cfile.exists():
+                st = WC.load(cfile, self.device)
+                self.w, self.resnets, self.xf_paths = st["w"], st["resnets"], st["xf_paths"]
+                self.temb_off = {k: tuple(v) for k, v in st["temb_off"].items()}
+                self.from_cache = True
+                return
+        self.from_cache = False
+        self._pack(sd, spec, device, dtype)
+        if cfile is not None:
+            WC.save(cfile, {"w": self.w, "resnets": self.resnets, "xf_paths": self.xf_paths,
+                            "temb_off": {k: list(v) for k, v in self.temb_off.items()}})
+
+    def _pack(self, sd: SD, spec: UNetSpec, device, dtype):
         pk = _Packer(sd, device, dtype)
         ch = spec.block_out_channels
         nb = len(ch)
@@ -181,11 +206,6 @@ class UNetEngine:
             ws.append(w)
             bs.append(b)
         W["temb_all"] = (torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous())
-        self.clip_state: Optional[dict] = None
-        self._persist: Dict[str, Dict[str, torch.Tensor]] = {}
-        self._graphs: Dict[tuple, dict] = {}
-        self.use_graphs = True
-        self._launches_per_forward = 0
 
     # ------------------------------------------------------------------------------------------------
     def _sinusoid(self, timesteps: torch.Tensor) -> torch.Tensor:

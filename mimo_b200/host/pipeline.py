@@ -151,9 +151,21 @@ class Pose2VideoPipeline:
             self._clip_image_processor = CLIPImageProcessor()
         return self._clip_image_processor.preprocess(ref_image.resize((224, 224)), return_tensors="pt").pixel_values
 
-    def _clip_embeds(self, ref_image: PIL.Image.Image) -> torch.Tensor:
+    def _clip(self):
+        """The caller's transformers.CLIPVisionModelWithProjection is a parameter container here: its forward runs on
+        the engine's kernels (mimo_b200/clip_engine.py), rebuilt when the parameters move or change dtype."""
+        from ..clip_engine import CLIPVisionEngine
         p = next(self.image_encoder.parameters())
-        return self.image_encoder(self._clip_pixels(ref_image).to(p.device, dtype=p.dtype)).image_embeds
+        key = (p.device, p.dtype, p.data_ptr())
+        if getattr(self, "_clip_engine_key", None) != key:
+            if p.device.type != "cuda":
+                raise MimoError("the CLIP image encoder must be on a CUDA (sm_100a) device: no CPU fallback")
+            self._clip_engine = CLIPVisionEngine(self.image_encoder.state_dict(), self.image_encoder.config, p.device, p.dtype)
+            self._clip_engine_key = key
+        return self._clip_engine
+
+    def _clip_embeds(self, ref_image: PIL.Image.Image) -> torch.Tensor:
+        return self._clip().image_embeds(self._clip_pixels(ref_image))
 
     def _vae(self):
         from .modules import AutoencoderKL as _OurVAE
@@ -229,8 +241,7 @@ class Pose2VideoPipeline:
         self.scheduler.set_timesteps(num_inference_steps, device="cpu")
         timesteps = [int(t) for t in self.scheduler.timesteps]
 
-        p = next(self.image_encoder.parameters())
-        emb = self.image_encoder(inp["clip_pixels"].to(p.device, dtype=p.dtype)).image_embeds.to(dtype)  # :378-385
+        emb = self._clip().image_embeds(inp["clip_pixels"]).to(dtype)  # :378-385
         ehs = emb.unsqueeze(1)
         if do_cfg:
             ehs = torch.cat([torch.zeros_like(ehs), ehs], dim=0)

@@ -138,6 +138,8 @@ SYMBOLS = {
     "mimo_softmax_rows": (C.c_int, [_VP, _I64, _I32, _I64, _I32, _VP]),
     "mimo_add": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _VP]),
     "mimo_silu": (C.c_int, [_VP, _VP, _I64, _I32, _VP]),
+    "mimo_quick_gelu": (C.c_int, [_VP, _VP, _I64, _I32, _VP]),
+    "mimo_composite_frame": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_double, _VP, _I64, _VP]),
     "mimo_cfg_ddim_step": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _I64, _F, _F, _F, _F, _F, _I32, _VP]),
 }
 # test hook, not part of the public header

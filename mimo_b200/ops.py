@@ -359,6 +359,30 @@ def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     return out
 
 
+def quick_gelu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty_like(x)
+    with _Call("elementwise", 1, 0.0, 2.0 * 2 * x.numel()):
+        L.check(L.load().mimo_quick_gelu(_ptr(x), _ptr(out), x.numel(), _dt(x), _stream()), "mimo_quick_gelu")
+    return out
+
+
+def composite_frame(canvas: torch.Tensor, bk: torch.Tensor, mask: torch.Tensor, *, occ: Optional[torch.Tensor] = None,
+                    vid: Optional[torch.Tensor] = None, prev: Optional[torch.Tensor] = None, factor: float = 0.0,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """run_edit.py:282-300 for one frame; uint8 [H, W, 3] images, float32 [H, W] mask, uint8 [H, W] occlusion."""
+    for t in (canvas, bk) + tuple(x for x in (occ, vid, prev) if x is not None):
+        assert t.dtype == torch.uint8 and t.is_contiguous() and t.is_cuda
+    assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.shape == canvas.shape[:2]
+    if out is None:
+        out = torch.empty_like(canvas)
+    px = canvas.shape[0] * canvas.shape[1]
+    with _Call("composite", 1, 0.0, float(px * (3 * (3 + (occ is not None) + (prev is not None)) + 4 + (occ is not None)))):
+        L.check(L.load().mimo_composite_frame(_ptr(canvas), _ptr(bk), _ptr(mask), _ptr(occ), _ptr(vid), _ptr(prev),
+                                              float(factor), _ptr(out), px, _stream()), "mimo_composite_frame")
+    return out
+
+
 def cfg_ddim_step(pred_uncond: torch.Tensor, pred_cond: torch.Tensor, latents: torch.Tensor, guidance: float,
                   sqrt_a_t: float, sqrt_1ma_t: float, sqrt_a_prev: float, sqrt_1ma_prev: float, *,
                   counter: Optional[torch.Tensor] = None, frame_stride: int = 0) -> torch.Tensor:

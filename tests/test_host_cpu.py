@@ -169,3 +169,44 @@ def test_conv_up2x_weight_packing_equals_interpolate_plus_conv():
                     src = xp[:, :, 1 + dy:1 + dy + h, 1 + dx:1 + dx + w]
                     out[:, :, a::2, b::2] += torch.einsum("oc,nchw->nohw", w4[2 * a + b, :, 2 * iy + ix], src)
     assert float((out - ref).abs().max()) < 1e-4
+
+
+def test_composite_oracle_and_mask_modes():
+    """The numpy restatement of run_edit.py:282-300 on a hand-checked pixel, and the 16-way feather-mask selection
+    (tools/util.py:393-437) of the host-side compositing helper."""
+    import numpy as np
+
+    from mimo_b200.host.composite import MASK_MODES, mask_mode
+    from oracle.composite_oracle import composite_frame
+    canvas = np.full((1, 1, 3), 200, np.uint8)
+    bk = np.full((1, 1, 3), 100, np.uint8)
+    m = np.full((1, 1), 0.25, np.float32)
+    assert composite_frame(canvas, bk, m)[0, 0, 0] == 125            # 200 * .25 + 100 * .75
+    occ = np.full((1, 1), 255, np.uint8)
+    vid = np.full((1, 1, 3), 7, np.uint8)
+    assert composite_frame(canvas, bk, m, occ, vid)[0, 0, 0] == 7    # fully occluded: the original frame wins
+    prev = np.full((1, 1, 3), 25, np.uint8)
+    assert composite_frame(canvas, bk, m, None, None, prev, 0.2)[0, 0, 0] == 45  # 25 * .8 + 125 * .2, truncated
+    W, H = 100, 50
+    assert MASK_MODES[mask_mode((0, 100, 0, 50), W, H)] == "up_down_left_right"
+    assert MASK_MODES[mask_mode((0, 100, 0, 40), W, H)] == "left_right_up"
+    assert MASK_MODES[mask_mode((10, 100, 0, 50), W, H)] == "up_down_right"
+    assert MASK_MODES[mask_mode((0, 60, 5, 50), W, H)] == "left_down"
+    assert MASK_MODES[mask_mode((10, 60, 5, 50), W, H)] == "down"
+    assert MASK_MODES[mask_mode((10, 60, 5, 45), W, H)] == "inner"
+
+
+def test_packed_weight_cache_container_round_trip(tmp_path):
+    from mimo_b200.host import weight_cache as WC
+    obj = {"w": {"a": (torch.randn(3, 4).half(), None), "b": {"C": 320, "l": [torch.ones(2), torch.zeros(1)]}},
+           "names": ["x", "y"], "off": {"p": [0, 5]}}
+    f = tmp_path / "t.safetensors"
+    WC.save(f, obj)
+    back = WC.load(f, "cpu")
+    assert torch.equal(back["w"]["a"][0], obj["w"]["a"][0]) and back["w"]["a"][1] is None
+    assert isinstance(back["w"]["a"], tuple) and back["w"]["b"]["C"] == 320 and back["names"] == ["x", "y"]
+    a = {"k": torch.arange(10000.0)}
+    b = {"k": torch.arange(10000.0)}
+    b["k"][5000] += 1  # a change between the sampled positions is caught only by the full hash
+    assert WC.fingerprint(a) == WC.fingerprint({"k": torch.arange(10000.0)})
+    assert WC.fingerprint(a, "x") != WC.fingerprint(a, "y")
