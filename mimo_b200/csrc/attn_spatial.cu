@@ -356,8 +356,10 @@ extern "C" int mimo_attn_spatial(const mimo_attn_params* p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nch = (a.dp + 63) / 64;
   const bool bf = p->dtype == MIMO_BF16;
-  // variant bit 16 selects the two-threads-per-row kernel (attn_spatial_pp2.cu) where it applies
-  if ((g_attn_variant & 16) && attn_pp2_supports(p->d)) return launch_attn_pp2(bf, tq, tk, tv, tbk, tbv, a, p->n, st);
+  // d + 1 <= 64 (the 64x64 level, d = 40: MUFU-bound): two softmax threads per row + row sum on the tensor pipe
+  // (attn_spatial_pp2.cu; measured 467 vs 429 TFLOP/s). Variant bit 16 forces it wherever it applies, bit 32 disables it.
+  if (attn_pp2_supports(p->d) && !(g_attn_variant & 32) && g_attn_variant != 1 && ((g_attn_variant & 16) || p->d + 1 <= 64))
+    return launch_attn_pp2(bf, tq, tk, tv, tbk, tbv, a, p->n, st);
   if (nch <= 2 && g_attn_variant != 1) return launch_attn_pp(bf, tq, tk, tv, tbk, tbv, a, p->n, st);
   if (nch == 1) return bf ? launch_attn<1, 2, true>(tq, tk, tv, tbk, tbv, a, grid, st)
                           : launch_attn<1, 2, false>(tq, tk, tv, tbk, tbv, a, grid, st);
