@@ -45,6 +45,20 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-4 polynomial
+// (max relative error 7.2e-6 in fp32 Horner form, 30x below the fp16 rounding of P), 2^n by adding n to the exponent
+// field. The magic constant 1.5 * 2^23 leaves round(x) in the low mantissa bits of t, and (t_bits << 23) is n << 23.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.009666374f, f, 0.055838343f);
+  p = fmaf(p, f, 0.24022348f);
+  p = fmaf(p, f, 0.69313675f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 template <int NCH, bool kBf16>
 __global__ void __launch_bounds__(kPP2Threads, 1)
 attn_spatial_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -279,6 +293,23 @@ attn_spatial_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       // ---- probabilities: 16 at a time straight into the swizzled A-operand row ----
       const float nm = -m_ref;
+      if (a.variant & 64) {
+        // a quarter of the exponentials on the FMA pipe: the MUFU pipe (16 ex2 / clk / SM) is the bound of this kernel
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x0 = fmaf(__uint_as_float(sv[c >> 1][(c & 1) * 16 + 2 * i]), sc, nm);
+            const float x1 = fmaf(__uint_as_float(sv[c >> 1][(c & 1) * 16 + 2 * i + 1]), sc, nm);
+            const float p0 = (i & 1) ? ex2_poly(x0) : ex2f(x0);
+            const float p1 = ex2f(x1);
+            pk[i] = C::pack(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(prow + (((2 * c) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(prow + (((2 * c + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[8];
@@ -290,6 +321,7 @@ attn_spatial_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
         *reinterpret_cast<uint4*>(prow + (((2 * c) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(prow + (((2 * c + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
       }
       if (j == 0 && x == 0) {
         __syncwarp();

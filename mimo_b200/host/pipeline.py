@@ -128,8 +128,10 @@ class Pose2VideoPipeline:
             kw = dict(timeout_ms=getattr(self, "_xchg_timeout_ms", 0))
             self._xchg_frame = (Exchange.create(plan.frame_group(), rank, {"A": tok, "B": tok}, self.device, group, **kw)
                                 if plan.frame_ways > 1 else None)
-            self._xchg_world = Exchange.create(list(range(world)), rank, {"S": n_my_windows * nb * 4 * fl * h * w * esz},
-                                               self.device, group, **kw)
+            # two gather sources used alternately: a source may only be rewritten once every peer has announced the NEXT
+            # exchange (= finished pulling this one), i.e. after one exchange in between (csrc/exchange.cu)
+            sz = n_my_windows * nb * 4 * fl * h * w * esz
+            self._xchg_world = Exchange.create(list(range(world)), rank, {"S0": sz, "S1": sz}, self.device, group, **kw)
             self._xchg_key = key
         return self._xchg_frame, self._xchg_world
 
@@ -309,7 +311,8 @@ class Pose2VideoPipeline:
         if plan:
             fl = len(win_inputs[0][1])
             den.xchg, xw = self._exchanges(plan, nb, len(my_windows), fl, h, w, dtype)
-            stage = xw.bufs["S"].view(len(my_windows), nb * 4 * fl * h * w, dtype)
+            stages = [xw.bufs[k].view(len(my_windows), nb * 4 * fl * h * w, dtype) for k in ("S0", "S1")]
+            stage = stages[0]
             gathered = torch.empty((world, len(my_windows), nb, 4, fl, h, w), dtype=dtype, device=device)
             gcols = next(c for c in (64, 32, 16, 8) if stage.numel() % c == 0)
             from .shard import gather_layout
@@ -322,10 +325,13 @@ class Pose2VideoPipeline:
             den.xchg = None
         for i, t in enumerate(timesteps):
             if plan:
+                par = getattr(xw, "parity", 0)  # alternates across steps AND clips
+                xw.parity = par ^ 1
+                stage = stages[par]
                 for j, (c, cl, bk_c, pose_in) in enumerate(win_inputs):
                     lat_in = torch.cat([latents[:, :, cl], bk_c], dim=1).repeat(nb, 1, 1, 1, 1)
                     stage[j].copy_(den.forward(lat_in, t, pose_in).reshape(-1))
-                xw.pull(2, "S", gathered.view(-1, gcols), 1, 1, stage.numel() // gcols, gcols)
+                xw.pull(2, ("S0", "S1")[par], gathered.view(-1, gcols), 1, 1, stage.numel() // gcols, gcols)
                 noise_pred = torch.zeros((rep, 4, F_, h, w), device=device, dtype=dtype)
                 for q, j, brs, fidx in scatter:
                     noise_pred[brs[0]:brs[-1] + 1] = noise_pred[brs[0]:brs[-1] + 1].index_add(2, fidx, gathered[q, j])

@@ -91,3 +91,44 @@ def test_sharded_clip_equals_single_gpu(world, tmp_path):
     keep = os.environ.get("MIMO_MGPU_JSON")
     if keep:
         Path(keep).write_text(json.dumps(res, indent=1))
+
+
+def test_cfg_branch_split_is_bit_identical():
+    """ShardPlan's CFG axis: evaluating one CFG branch alone (batch 1, what a CFG-sharded GPU does) must give exactly the
+    rows the two-branch forward gives - every kernel is per row / per image, nothing may depend on the batch."""
+    from mimo_b200 import engine as E
+    from oracle import torch_oracle as O
+    dev = torch.device("cuda")
+    widths, f, hw, seed = (128, 256, 512, 512), 24, 16, 41
+    cfg = O.UNetConfig(block_out_channels=widths)
+    sd_den, sd_ref = O.make_denoising_unet_sd(cfg, seed), O.make_reference_unet_sd(cfg, seed + 1)
+    g = torch.Generator().manual_seed(seed)
+    ref_lat = torch.randn(1, 4, hw, hw, generator=g).repeat(2, 1, 1, 1).half().to(dev)
+    emb = torch.randn(1, 1, 768, generator=g)
+    ehs = torch.cat([torch.zeros_like(emb), emb]).half().to(dev)
+    x = torch.randn(1, 8, f, hw, hw, generator=g).half().to(dev)
+    pose = (torch.randn(f * hw * hw, widths[0], generator=g) * 0.1).half().to(dev)
+    den = E.UNetEngine(sd_den, E.UNetSpec(block_out_channels=widths), dev)
+    ref = E.UNetEngine(sd_ref, E.UNetSpec(block_out_channels=widths, in_channels=4, motion=False, out_head=False), dev)
+    den.use_graphs = False
+    banks = ref.write_banks(ref_lat, ehs, den)
+
+    def run(branches):
+        den.begin_clip(ehs, banks, cfg=True, frames=f, branches=branches)
+        den.taps = {}
+        nb = len(branches)
+        out = den.forward(x.repeat(nb, 1, 1, 1, 1), 499, pose.repeat(nb, 1).contiguous()).clone()
+        taps, den.taps = den.taps, None
+        return out, taps
+
+    both, tb = run((0, 1))
+    bad = []
+    for br in (0, 1):
+        one, t1 = run((br,))
+        for name in tb:
+            if name in t1 and not torch.equal(tb[name][br * f:(br + 1) * f], t1[name]):
+                bad.append((br, name, float((tb[name][br * f:(br + 1) * f] - t1[name]).abs().max())))
+                break
+        if not torch.equal(both[br:br + 1], one):
+            bad.append((br, "output", float((both[br:br + 1].float() - one.float()).abs().max())))
+    assert not bad, f"first differing block per branch: {bad}"
