@@ -344,7 +344,7 @@ def run_ours(args):
         from mimo_b200.host.shard import ShardPlan
         from mimo_b200.host.context import uniform
         wins = list(uniform(0, DDIM_STEPS, FRAMES, 24, 1, 4))
-        pl = ShardPlan.make(world, 0, True, len(wins), len(wins[0]))
+        pl = ShardPlan.make(world, 0, True, len(wins), len(wins[0]), min_tokens=(HEIGHT // 64) * (WIDTH // 64))
         par = (f"{world} GPUs = CFG branches x{pl.cfg_ways} * windows x{pl.win_ways} * frames x{pl.frame_ways}; "
                "frames<->pixels exchange over NVLink peer memory (mimo_exchange), no NCCL on the data path")
     line = {

@@ -285,7 +285,13 @@ class Pose2VideoPipeline:
             from .shard import ShardPlan
             if len({len(c) for c in windows}) != 1:
                 raise NotImplementedError("context windows of different lengths cannot be sharded")
-            plan = ShardPlan.make(world, rank, do_cfg, len(windows), len(windows[0]))
+            hmin = max(1, h >> (len(self.denoising_unet.config.block_out_channels) - 1))
+            wmin = max(1, w >> (len(self.denoising_unet.config.block_out_channels) - 1))
+            plan = ShardPlan.make(world, rank, do_cfg, len(windows), len(windows[0]), min_tokens=hmin * wmin)
+            forced = getattr(self, "force_plan", None)  # (cfg_ways, win_ways, frame_ways): tests exercise every axis
+            if forced is not None:
+                assert forced[0] * forced[1] * forced[2] == world
+                plan = ShardPlan(world, rank, *forced)
         branches = plan.branches(do_cfg) if plan else tuple(range(rep))
         nb = len(branches)
 

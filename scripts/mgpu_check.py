@@ -77,22 +77,31 @@ def main():
     rel = lambda a, b: float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
     ok, rows = True, []
     size = 128
-    for F_, guidance in ((24, 3.5), (24, 1.0), (48, 3.5), (48, 1.0)):
+    cases = [(24, 3.5, None), (24, 1.0, None), (48, 3.5, None), (48, 1.0, None)]
+    if world % 2 == 0:  # the CFG axis (chosen last by ShardPlan.make) forced on, with whatever is left on frames
+        cases += [(24, 3.5, (2, 1, world // 2)), (48, 3.5, (2, 1, world // 2))]
+    for F_, guidance, forced in cases:
+        pipe.force_plan = forced
         ref_img, poses, bks = _pil_inputs(F_, size, seed)
         run = lambda: pipe(ref_img, poses, bks, size, size, F_, 2, guidance, generator=torch.manual_seed(42)).videos
         pipe.enable_sharding(0, 1)
+        pipe.force_plan = None
         a = run()
         lat_a = pipe.last_latents.clone()
         a2 = run()
         same = bool(torch.equal(lat_a, pipe.last_latents) and torch.equal(a, a2))
         pipe.enable_sharding(rank, world, exchange_timeout_ms=20000)
+        pipe.force_plan = forced
         b1 = run()
         lat_b = pipe.last_latents.clone()
         b2 = run()
         b3 = run()  # eager, capture, replay
         same_sh = bool(torch.equal(lat_b, pipe.last_latents) and torch.equal(b1, b3) and torch.equal(b1, b2))
         from mimo_b200.host.shard import ShardPlan
-        plan = ShardPlan.make(world, rank, guidance > 1.0, 1 if F_ <= 24 else len(range(0, F_, 20)), 24)
+        plan = ShardPlan.make(world, rank, guidance > 1.0, 1 if F_ <= 24 else len(range(0, F_, 20)), 24,
+                              min_tokens=(size // 64) ** 2)
+        if forced is not None:
+            plan = ShardPlan(world, rank, *forced)
         row = {"F": F_, "cfg": guidance > 1.0, "plan": [plan.cfg_ways, plan.win_ways, plan.frame_ways],
                "single_gpu_bit_identical_run_to_run": same, "sharded_bit_identical_run_to_run": same_sh,
                "latents_rel_l2": rel(lat_b, lat_a), "latents_max_abs": float((lat_b.float() - lat_a.float()).abs().max()),

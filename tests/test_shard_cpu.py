@@ -46,13 +46,16 @@ def test_plan_covers_every_window_branch_frame_exactly_once(world, F_, do_cfg):
 
 
 def test_plan_choices_for_the_baseline_configs():
-    mk = lambda world, nwin, cfg=True: ShardPlan.make(world, 0, cfg, nwin, 24)
-    assert (mk(2, 1).cfg_ways, mk(2, 1).win_ways, mk(2, 1).frame_ways) == (2, 1, 1)   # CFG only: no exchange at all
-    assert (mk(4, 1).cfg_ways, mk(4, 1).frame_ways) == (2, 2)
-    assert (mk(8, 1).cfg_ways, mk(8, 1).frame_ways) == (2, 4)                         # configs[2]
-    assert (mk(8, 3).cfg_ways, mk(8, 3).win_ways, mk(8, 3).frame_ways) == (2, 1, 4)   # configs[3]: 48 frames
-    assert (mk(8, 4).cfg_ways, mk(8, 4).win_ways, mk(8, 4).frame_ways) == (2, 4, 1)   # configs[4]: 64 frames
-    assert (mk(8, 1, False).cfg_ways, mk(8, 1, False).frame_ways) == (1, 8)
+    mk = lambda world, nwin, cfg=True, **kw: (lambda p: (p.cfg_ways, p.win_ways, p.frame_ways))(
+        ShardPlan.make(world, 0, cfg, nwin, 24, **kw))
+    assert mk(2, 1) == (1, 1, 2)                  # frames before the (unbalanced) CFG pair
+    assert mk(4, 1) == (1, 1, 4)
+    assert mk(8, 1) == (1, 1, 8)                  # configs[2]: 3 frames x 2 branches per GPU
+    assert mk(8, 3) == (1, 1, 8)                  # configs[3]: 48 frames = 3 windows, windows do not divide 8
+    assert mk(8, 4) == (1, 4, 2)                  # configs[4]: 64 frames = 4 windows x 2 frame halves
+    assert mk(8, 1, False) == (1, 1, 8)
+    assert mk(16, 1) == (2, 1, 8)                 # 24 frames do not split 16 ways: the CFG pair takes the last factor
+    assert mk(8, 1, min_tokens=4) == (2, 1, 4)    # a 2x2 coarsest level cannot be cut into 8 pixel shards
     with pytest.raises(NotImplementedError):
         ShardPlan.make(5, 0, False, 1, 24)
 
