@@ -10,6 +10,10 @@
 //     so O[:, d] accumulates sum_k P[q, k] of exactly the fp16-rounded P that multiplies V - no FADD per element, no
 //     cross-thread sum, and lazy rescaling treats it like any other O column;
 //   * P is packed and stored 16 values at a time straight out of the S registers (no second register array).
+// Measured on B200 (profiles/r02_attn_ab*.log, n = 48, 4096 queries, 8192 / 4096 keys, d = 40): 3.34 ms vs 3.62 ms for the
+// one-thread-per-row kernel. Also tried here and dropped: a degree-4 polynomial exp2 on the FMA pipe for a quarter of the
+// elements (3.48 ms: with the MUFU work already spread over 16 warps the kernel is issue-bound, the extra 8 instructions
+// per offloaded element cost more than the MUFU slots they free), and ex2.approx.f16x2 (two MUFU.EX2.F16 in SASS).
 //
 //   warp 0        : TMA   - Q tiles A and B once; K / V tiles in rings shared by both query tiles
 //   warp 1 / 3    : MMA   - warp 1 drives query tile A, warp 3 tile B (whole warp + one elected lane)
@@ -43,20 +47,6 @@ __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// 2^x on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-4 polynomial
-// (max relative error 7.2e-6 in fp32 Horner form, 30x below the fp16 rounding of P), 2^n by adding n to the exponent
-// field. The magic constant 1.5 * 2^23 leaves round(x) in the low mantissa bits of t, and (t_bits << 23) is n << 23.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(0.009666374f, f, 0.055838343f);
-  p = fmaf(p, f, 0.24022348f);
-  p = fmaf(p, f, 0.69313675f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
 template <int NCH, bool kBf16>
@@ -293,23 +283,6 @@ attn_spatial_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       // ---- probabilities: 16 at a time straight into the swizzled A-operand row ----
       const float nm = -m_ref;
-      if (a.variant & 64) {
-        // a quarter of the exponentials on the FMA pipe: the MUFU pipe (16 ex2 / clk / SM) is the bound of this kernel
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x0 = fmaf(__uint_as_float(sv[c >> 1][(c & 1) * 16 + 2 * i]), sc, nm);
-            const float x1 = fmaf(__uint_as_float(sv[c >> 1][(c & 1) * 16 + 2 * i + 1]), sc, nm);
-            const float p0 = (i & 1) ? ex2_poly(x0) : ex2f(x0);
-            const float p1 = ex2f(x1);
-            pk[i] = C::pack(p0, p1);
-          }
-          *reinterpret_cast<uint4*>(prow + (((2 * c) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(prow + (((2 * c + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[8];
@@ -321,7 +294,6 @@ attn_spatial_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
         *reinterpret_cast<uint4*>(prow + (((2 * c) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(prow + (((2 * c + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
       }
       if (j == 0 && x == 0) {
         __syncwarp();

@@ -416,26 +416,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
             } else {
               const float4 b0 = cb[2 * q], b1 = cb[2 * q + 1];
-              f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), scale, b0.x);
-              f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), scale, b0.y);
-              f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), scale, b0.z);
-              f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), scale, b0.w);
-              f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), scale, b1.x);
-              f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), scale, b1.y);
-              f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), scale, b1.z);
-              f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), scale, b1.w);
-            }
-            if constexpr (kMode == 2) {
-              if (rv && col0 + q * 8 < N) {
-                const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + col0 + q * 8));
-                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+              float cst[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              if constexpr (kMode == 2) {
+                // the per-row vector joins the column constants FIRST, exactly as load_consts() pre-sums them when a
+                // tile lies inside one group: acc + (bias + vec) either way, so a tile that straddles two CFG branches
+                // and one that does not round identically (sharded == un-sharded, bit for bit)
+                if (rv && col0 + q * 8 < N) {
+                  const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + col0 + q * 8));
+                  const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 t = C::unpack(bw[j]);
-                  f[2 * j] = fmaf(t.x, scale, f[2 * j]);
-                  f[2 * j + 1] = fmaf(t.y, scale, f[2 * j + 1]);
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 t = C::unpack(bw[j]);
+                    cst[2 * j] = fmaf(t.x, scale, cst[2 * j]);
+                    cst[2 * j + 1] = fmaf(t.y, scale, cst[2 * j + 1]);
+                  }
                 }
               }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[q * 8 + j]), scale, cst[j]);
             }
             if constexpr (kRes) {
               const uint4 rr = *reinterpret_cast<const uint4*>(rrow + ((q ^ sw) << 4));
