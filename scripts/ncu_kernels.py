@@ -75,6 +75,18 @@ def norm(n=48, hw=4096, c=320):
         ops.layernorm(x, g, b)
 
 
+def convup(n=48, h=32, c=640):
+    x = torch.randn(n * h * h, c, device=dev).half()
+    w4 = ops.pack_conv_up2x_weight(torch.randn(c, c, 3, 3, device=dev).half() / 70)
+    b = torch.randn(c, device=dev).half()
+    for _ in range(2):
+        ops.conv_up2x(x, w4, n, h, h, bias=b)
+
+
+def ffo(M=49152, N=640, K=2560):
+    gemm(M, N, K)
+
+
 def temporal(hw=4096, d=40):
     C = 8 * d
     qkv = torch.randn(48 * hw, 3 * C, device=dev).half()

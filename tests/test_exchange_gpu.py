@@ -87,7 +87,7 @@ def test_sharded_clip_equals_single_gpu(world, tmp_path):
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, "sharded clip differs from the single-GPU clip (see stdout)"
     res = json.loads(out.read_text())
-    assert res["ok"] and all(c["latents_rel_l2"] <= 2e-3 for c in res["cases"])
+    assert res["ok"] and all(c["latents_rel_l2"] <= 5e-3 and c["videos_rel_l2"] <= 2e-3 for c in res["cases"])
     keep = os.environ.get("MIMO_MGPU_JSON")
     if keep:
         Path(keep).write_text(json.dumps(res, indent=1))
