@@ -91,3 +91,47 @@ def test_conv_up2x_matches_interpolate_plus_conv(probe):
         got = ops.conv_up2x(xr, ops.pack_conv_up2x_weight(W), n, h, w, bias=b, act=act)
         got = got.reshape(n, 2 * h, 2 * w, -1)[..., :cout].permute(0, 3, 1, 2)
         assert probe.report(f"conv_up2x n={n} {h}x{w} {cin}->{cout}", got, ref, tol=2e-3)
+
+
+def test_split_k_small_m_long_k(probe):
+    """Split-K (fp32 partials + fixed-order reduction) for the small-M / long-K problems a frame-sharded GPU sees at the
+    8x8 and 16x16 levels: against fp32 torch, against the un-split kernel, and bit-identical run to run."""
+    import torch.nn.functional as F
+
+    from mimo_b200 import lib as L
+    from mimo_b200 import ops
+    lib = L.load()
+    torch.manual_seed(5)
+    # GEMM with the whole epilogue: bias + per-group row vector + residual + SiLU
+    M, N, K = 384, 1280, 5120
+    a = (torch.randn(M, K, device="cuda") / 8).half()
+    w = (torch.randn(N, K, device="cuda") / 9).half()
+    b = torch.randn(N, device="cuda").half()
+    rv = torch.randn(2, N, device="cuda").half()
+    r = torch.randn(M, N, device="cuda").half()
+    ref = F.silu(a.float() @ w.float().t() + b.float() + rv.float().repeat_interleave(192, 0) + r.float())
+    lib.mimo_debug_splitk(1)
+    got = ops.gemm(a, w, bias=b, rowvec=rv, rows_per_group=192, residual=r, act=L.ACT_SILU)
+    got2 = ops.gemm(a, w, bias=b, rowvec=rv, rows_per_group=192, residual=r, act=L.ACT_SILU)
+    lib.mimo_debug_splitk(0)
+    plain = ops.gemm(a, w, bias=b, rowvec=rv, rows_per_group=192, residual=r, act=L.ACT_SILU)
+    lib.mimo_debug_splitk(1)
+    assert torch.equal(got, got2)
+    assert probe.report("split-K gemm 384x1280x5120", got, ref) and probe.report("  vs un-split", got, plain.float(), tol=1e-3)
+    # 3x3 convolution, two sources (up-block concat), time-embedding row vector, residual
+    n, h, c0, c1, co = 6, 8, 1280, 1280, 1280
+    x0 = torch.randn(n * h * h, c0, device="cuda").half()
+    x1 = torch.randn(n * h * h, c1, device="cuda").half()
+    Wc = (torch.randn(co, c0 + c1, 3, 3, device="cuda") / (3 * (c0 + c1) ** 0.5)).half()
+    bias = torch.randn(co, device="cuda").half()
+    tv = torch.randn(2, co, device="cuda").half()
+    res = torch.randn(n * h * h, co, device="cuda").half()
+    xin = torch.cat([x0, x1], 1).float().reshape(n, h, h, c0 + c1).permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, Wc.float(), bias.float(), padding=1).permute(0, 2, 3, 1).reshape(n * h * h, co)
+    ref = ref + tv.float().repeat_interleave(3 * h * h, 0) + res.float()
+    wp = ops.pack_conv3x3_weight(Wc)
+    got = ops.conv3x3(x0, wp, n, h, h, x1=x1, bias=bias, rowvec=tv, rows_per_group=3 * h * h, residual=res)
+    lib.mimo_debug_splitk(0)
+    plain = ops.conv3x3(x0, wp, n, h, h, x1=x1, bias=bias, rowvec=tv, rows_per_group=3 * h * h, residual=res)
+    lib.mimo_debug_splitk(1)
+    assert probe.report("split-K conv 6x8x8 2560->1280", got, ref) and probe.report("  vs un-split", got, plain.float(), tol=1e-3)
