@@ -257,11 +257,26 @@ class Pose2VideoPipeline:
         bk_px = uint8_to_tensor(inp["bk_unique_u8"], True).to(dtype)
         pose_px = uint8_to_tensor(inp["pose_u8"], False).permute(1, 0, 2, 3).unsqueeze(0).to(dtype)  # [1, 3, F, H, W]
         ref_latents = enc.encode_mean(ref_px) * 0.18215  # :424-431
-        bk_lat = (enc.encode_mean(bk_px) * 0.18215)[inp["bk_inverse"].to(device)]
+        rank, world, group = self._shard
+        n_bk = bk_px.shape[0]
+        if world > 1 and n_bk >= world:
+            # edit mode: one distinct background per frame (run_edit.py:232-238) - every GPU encodes its share, one
+            # all-gather per clip (per-image arithmetic: identical to encoding them all here)
+            import torch.distributed as dist
+            per = -(-n_bk // world)
+            lo, hi = min(rank * per, n_bk), min((rank + 1) * per, n_bk)
+            mine = torch.zeros((per, 4, h, w), device=device, dtype=dtype)
+            if hi > lo:
+                mine[:hi - lo] = enc.encode_mean(bk_px[lo:hi].contiguous()).to(dtype)
+            every = torch.empty((world * per, 4, h, w), device=device, dtype=dtype)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            bk_mean = every[:n_bk]
+        else:
+            bk_mean = enc.encode_mean(bk_px)
+        bk_lat = (bk_mean * 0.18215)[inp["bk_inverse"].to(device)]
         vid_bk = bk_lat.permute(1, 0, 2, 3).unsqueeze(0).to(dtype).contiguous()  # [1, 4, F, h, w]  :434-443
         mark("vae_encode")
 
-        rank, world, group = self._shard
         if world > 1:
             import torch.distributed as dist
             if F_ % world == 0:  # pose features: each rank computes its frames, then all-gather [F, hw, 320]

@@ -24,6 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--full-width", action="store_true", help="full SD1.5 width instead of the reduced test width")
+    ap.add_argument("--frames", type=int, nargs="*", default=None, help="only the cases with these frame counts")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -76,9 +77,11 @@ def main():
     rel = lambda a, b: float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
     ok, rows = True, []
     size = 128 if world <= 4 else 256  # the coarsest UNet level, (size / 64)^2 tokens, must split over the frame group
-    cases = [(24, 3.5, None), (24, 1.0, None), (48, 3.5, None), (48, 1.0, None)]
+    cases = [(24, 3.5, None), (24, 1.0, None), (48, 3.5, None), (48, 1.0, None), (64, 3.5, None)]  # 64: 4 windows
     if world % 2 == 0:  # the CFG axis (chosen last by ShardPlan.make) forced on, with whatever is left on frames
         cases += [(24, 3.5, (2, 1, world // 2)), (48, 3.5, (2, 1, world // 2))]
+    if args.frames:
+        cases = [c for c in cases if c[0] in args.frames]
     for F_, guidance, forced in cases:
         pipe.force_plan = forced
         ref_img, poses, bks = _pil_inputs(F_, size, seed)
@@ -97,7 +100,8 @@ def main():
         b3 = run()  # eager, capture, replay
         same_sh = bool(torch.equal(lat_b, pipe.last_latents) and torch.equal(b1, b3) and torch.equal(b1, b2))
         from mimo_b200.host.shard import ShardPlan
-        plan = ShardPlan.make(world, rank, guidance > 1.0, 1 if F_ <= 24 else len(range(0, F_, 20)), 24,
+        from mimo_b200.host.context import uniform
+        plan = ShardPlan.make(world, rank, guidance > 1.0, len(list(uniform(0, 2, F_, 24, 1, 4))), 24,
                               min_tokens=(size // 64) ** 2)
         if forced is not None:
             plan = ShardPlan(world, rank, *forced)
