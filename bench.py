@@ -311,6 +311,7 @@ def run_ours(args):
     try:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as tp:
+            sync()  # CUPTI start-up differs per rank: this barrier absorbs the skew, not the clip's first collective
             pipe.sample_tensors(dev_in, DDIM_STEPS, GUIDANCE)
             torch.cuda.synchronize()
         rows = {}
@@ -320,6 +321,8 @@ def run_ours(args):
                 us = getattr(ev, "cuda_time_total", 0.0)
             if us <= 0:
                 continue
+            if "AllReduce" in ev.key:
+                continue  # the barrier above
             nm = ev.key.replace("void ", "").split("(")[0]
             nm = nm if len(nm) <= 72 else nm[:72]
             r = rows.setdefault(nm, [0.0, 0])
