@@ -460,6 +460,7 @@ def _unet_parity(cfg_widths, f, hw, seed, taps=True, tol=3e-2):
                 e = rel_err(den.taps[name], ov)
                 flag = "" if e < tol else "   <<<<<<"
                 print(f"    tap {name:40s} rel_l2={e:.3e}{flag}")
+                ok &= e < tol  # every block output is held to the same bound as the network output
     ok &= report(f"denoising_unet widths={cfg_widths} f={f} latent={hw}", got, want, tol=tol)
     return ok
 
