@@ -479,7 +479,7 @@ class UNetEngine:
         sample = sample.contiguous()
         if not self.use_graphs or self.taps is not None or ops.PROFILE is not None:
             return self._forward_impl(sample, emb, pose_nhwc)
-        key = (tuple(sample.shape), sample.dtype, pose_nhwc is not None, st["bank_index"].data_ptr())
+        key = (tuple(sample.shape), sample.dtype, pose_nhwc is not None, st["bank_index"].data_ptr(), id(self.xchg))
         g = self._graphs.get(key)
         if g is None:
             g = {"calls": 0}

@@ -111,7 +111,7 @@ class Pose2VideoPipeline:
         per-window predictions are all-gathered the same way once per step, so every rank holds the whole clip's
         latents (tiny); pose features and decoded frames are computed sharded and gathered once per clip."""
         self._shard = (rank, world, group)
-        self._xchg_key, self._xchg_frame, self._xchg_world = None, None, None
+        self._xchg_key = None  # the next clip re-creates the peer buffers (and frees the old ones, collectively)
         self._xchg_timeout_ms = exchange_timeout_ms
 
     enable_frame_sharding = enable_sharding  # round-1 name
@@ -122,6 +122,12 @@ class Pose2VideoPipeline:
         rank, world, group = self._shard
         key = (plan, nb, n_my_windows, fl, h, w, dtype)
         if getattr(self, "_xchg_key", None) != key:
+            # captured forwards hold the old buffers' addresses: drop them before the buffers go away
+            self.denoising_unet.engine()._graphs.clear()
+            for old in (getattr(self, "_xchg_frame", None), getattr(self, "_xchg_world", None)):
+                if old is not None:
+                    old.destroy(group)
+            self._xchg_frame = self._xchg_world = None
             esz = torch.empty((), dtype=dtype).element_size()
             c0 = self.denoising_unet.config.block_out_channels[0]
             tok = nb * fl * h * w * c0 * esz  # the widest token tensor of a forward: the first level's
@@ -343,6 +349,8 @@ class Pose2VideoPipeline:
             for c in windows:
                 counter_all[c] = counter_all[c] + 1
         else:
+            if den.xchg is not None:
+                den._graphs.clear()  # graphs captured with exchange nodes must not serve an un-sharded run
             den.xchg = None
         for i, t in enumerate(timesteps):
             if plan:

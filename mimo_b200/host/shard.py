@@ -198,6 +198,25 @@ class Exchange:
         pbs = alloc_peer_buffers([4 * L.MAX_PEERS] + [sizes[k] for k in names], members, rank, device, group)
         return Exchange(len(members), list(members).index(rank), pbs[0], dict(zip(names, pbs[1:])), device, **kw)
 
+    def destroy(self, group=None) -> None:
+        """Collective: unmap the peers' buffers, then (after everyone has unmapped) free this member's own. Nothing may
+        still be queued on these buffers - in particular no captured CUDA graph may be replayed afterwards."""
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        pbs = [self.flags] + list(self.bufs.values())
+        if not all(pb._owned for pb in pbs):
+            return
+        dist.barrier(group)
+        for pb in pbs:
+            for s, ptr in enumerate(pb.peer_ptrs):
+                if s != self.r:
+                    L.check(L.load().mimo_peer_close(C.c_void_p(ptr)), "mimo_peer_close")
+        dist.barrier(group)
+        for pb in pbs:
+            pb.bytes = None
+            L.check(L.load().mimo_peer_free(C.c_void_p(pb.ptr)), "mimo_peer_free")
+            pb._owned = False
+
     def pull(self, mode: int, name: str, dst: torch.Tensor, b: int, fl: int, hw: int, Cdim: int,
              residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         from .. import ops
