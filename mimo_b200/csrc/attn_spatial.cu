@@ -59,6 +59,8 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int q_tile = blockIdx.x;
   const int h = blockIdx.y;
   const int n = blockIdx.z;
+  pdl_launch_dependents();
+  pdl_wait();
   const int bidx = __shfl_sync(0xffffffffu, a.bank_index ? a.bank_index[n] : -1, 0);
   const int T = a.n_self_tiles + (bidx >= 0 ? a.n_bank_tiles : 0);
 
@@ -286,8 +288,8 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn)", e);
     attr_done = true;
   }
-  kern<<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(q, k, v, bk, bv, a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(kern, grid, dim3(kAttnThreads), Cfg::kSmemBytes, st, q, k, v, bk, bv, a);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("attn launch", e);
   return MIMO_OK;
 }

@@ -81,18 +81,15 @@ attn_spatial_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int q_pair = blockIdx.x;
   const int h = blockIdx.y;
   const int n = blockIdx.z;
-  const int bidx = __shfl_sync(0xffffffffu, a.bank_index ? a.bank_index[n] : -1, 0);
-  const int T = a.n_self_tiles + (bidx >= 0 ? a.n_bank_tiles : 0);
+  pdl_launch_dependents();
   const int dpv = (a.d + 1 + 15) / 16 * 16;  // O columns: d value channels + the ones column, rounded to the MMA's N step
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    if (bidx >= 0) {
-      tma_prefetch_desc(&tmBK);
-      tma_prefetch_desc(&tmBV);
-    }
+    tma_prefetch_desc(&tmBK);
+    tma_prefetch_desc(&tmBV);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
@@ -117,6 +114,9 @@ attn_spatial_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   // columns: S_A [0,128)  S_B [128,256)  O_A [256,384)  O_B [384,512)
+  pdl_wait();  // the prologue above touched only shared memory / TMEM / kernel parameters
+  const int bidx = __shfl_sync(0xffffffffu, a.bank_index ? a.bank_index[n] : -1, 0);
+  const int T = a.n_self_tiles + (bidx >= 0 ? a.n_bank_tiles : 0);
 
   if (warp < 4) {
     if (warp == 0 && lane == 0) {
@@ -377,8 +377,8 @@ static int launch_pp2(const CUtensorMap& q, const CUtensorMap& k, const CUtensor
     attr_done = true;
   }
   dim3 grid((a.lq + 2 * BQ - 1) / (2 * BQ), a.heads, n);
-  kern<<<grid, kPP2Threads, Cfg::kSmem, st>>>(q, k, v, bk, bv, a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(kern, grid, dim3(kPP2Threads), Cfg::kSmem, st, q, k, v, bk, bv, a);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("attn_pp2 launch", e);
   return MIMO_OK;
 }

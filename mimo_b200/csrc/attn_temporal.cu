@@ -65,6 +65,8 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 // turns the row pitch and every fragment address into immediates; D = 0: generic (runtime) geometry.
 template <bool kBf16, int D, int HG>
 __global__ void __launch_bounds__(1024) attn_temporal_kernel(TemporalArgs a_in) {
+  pdl_launch_dependents();
+  pdl_wait();
   TemporalArgs a = a_in;
   if constexpr (D > 0) {
     a.d = D;
@@ -306,8 +308,7 @@ extern "C" int mimo_attn_temporal(const mimo_attn_temporal_params* p, void* stre
       if (ea != cudaSuccess) return ea;
       attr_done[id] = true;
     }
-    kern<<<grid, threads, smem, st>>>(a);
-    return cudaSuccess;
+    return launch_k(kern, dim3(grid), dim3(threads), smem, st, a);
   };
   const bool bf = p->dtype == MIMO_BF16;
   if (a.d == 40 && hg == 8)

@@ -46,6 +46,9 @@ int ensure_device() {
 }
 int num_sms() { return g_num_sms; }
 
+static bool g_pdl = true;
+bool pdl_enabled() { return g_pdl; }
+
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 int encode_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims,
@@ -158,4 +161,9 @@ extern "C" int mimo_peer_close(void* ptr) {
 extern "C" int mimo_peer_free(void* ptr) {
   cudaError_t e = cudaFree(ptr);
   return e == cudaSuccess ? MIMO_OK : mimo::set_cuda_error("mimo_peer_free", e);
+}
+
+extern "C" int mimo_debug_pdl(int on) {
+  mimo::g_pdl = on != 0;
+  return 0;
 }

@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(kXchgThreads, 2) xchg_pull_kernel(XchgArgs a) 
   __shared__ unsigned s_epoch;
   __shared__ const uint4* s_src[MIMO_MAX_PEERS];
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();  // the source buffer was written by the previous kernel(s) of this stream
   if (tid == 0) s_epoch = *reinterpret_cast<volatile unsigned*>(a.ctl);
   if (tid < a.G) s_src[tid] = static_cast<const uint4*>(a.src[tid]);
   __syncthreads();
@@ -208,11 +210,10 @@ extern "C" int mimo_exchange(const mimo_exchange_params* p, void* stream) {
   if (grid > units) grid = units;
   if (grid < 2) grid = 2;  // the two announcing blocks
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == MIMO_BF16)
-    xchg_pull_kernel<true><<<static_cast<unsigned>(grid), kXchgThreads, 0, st>>>(a);
-  else
-    xchg_pull_kernel<false><<<static_cast<unsigned>(grid), kXchgThreads, 0, st>>>(a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = p->dtype == MIMO_BF16
+                      ? launch_k(xchg_pull_kernel<true>, dim3(static_cast<unsigned>(grid)), dim3(kXchgThreads), 0, st, a)
+                      : launch_k(xchg_pull_kernel<false>, dim3(static_cast<unsigned>(grid)), dim3(kXchgThreads), 0, st, a);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("exchange launch", e);
   return MIMO_OK;
 }

@@ -111,6 +111,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::kBarBytes);  // [2][256]
 
+  pdl_launch_dependents();
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int num_tiles = num_m_tiles * num_n_tiles * g.splits;
@@ -152,6 +153,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();  // everything above touched only shared memory / TMEM / the kernel parameters
 
   // tile -> coordinates of its first output row / pixel
   auto tile_origin = [&](int m_tile, int& x0, int& y0, int& n0) {
@@ -616,6 +618,8 @@ splitk_reduce_kernel(const float* __restrict__ part, int splits, long long M, in
                      long long ldo) {
   using C = Cvt<kBf16>;
   using T = typename C::T;
+  pdl_launch_dependents();
+  pdl_wait();
   const int nv = N >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= M * nv) return;
@@ -691,8 +695,9 @@ static int launch_cfg(const Maps& m, int M, int N, int mt, int nt, int nkb, cons
   }
   const int tiles = mt * nt;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(m.a0, m.a1, m.b, m.out, m.res, M, N, mt, nt, nkb, g, ep);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, st, m.a0, m.a1, m.b, m.out, m.res, M, N, mt,
+                           nt, nkb, g, ep);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("gemm launch", e);
   return MIMO_OK;
 }
@@ -771,13 +776,12 @@ static int launch_reduce(int dtype, const float* part, int splits, long long M, 
   const unsigned blocks = div_up(total, 256);
   const long long rpg = e.rows_per_group > 0 ? e.rows_per_group : 1;
   const long long ldr = e.ld_rowvec > 0 ? e.ld_rowvec : N;
-  if (dtype == MIMO_BF16)
-    splitk_reduce_kernel<true><<<blocks, 256, 0, st>>>(part, splits, M, N, e.bias, e.rowvec, rpg, ldr, e.residual, e.ld_res,
-                                                       e.scale, e.act, out, ldo);
-  else
-    splitk_reduce_kernel<false><<<blocks, 256, 0, st>>>(part, splits, M, N, e.bias, e.rowvec, rpg, ldr, e.residual, e.ld_res,
-                                                        e.scale, e.act, out, ldo);
-  cudaError_t err = cudaGetLastError();
+  cudaError_t err = dtype == MIMO_BF16
+                        ? launch_k(splitk_reduce_kernel<true>, dim3(blocks), dim3(256), 0, st, part, splits, M, N, e.bias,
+                                   e.rowvec, rpg, ldr, e.residual, static_cast<long long>(e.ld_res), e.scale, e.act, out, ldo)
+                        : launch_k(splitk_reduce_kernel<false>, dim3(blocks), dim3(256), 0, st, part, splits, M, N, e.bias,
+                                   e.rowvec, rpg, ldr, e.residual, static_cast<long long>(e.ld_res), e.scale, e.act, out, ldo);
+  if (err == cudaSuccess) err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error("split-K reduce launch", err);
   return MIMO_OK;
 }

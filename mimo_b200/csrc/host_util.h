@@ -20,4 +20,25 @@ int encode_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const u
 
 inline unsigned div_up(long long a, long long b) { return static_cast<unsigned>((a + b - 1) / b); }
 
+// Programmatic dependent launch (test hook mimo_debug_pdl, default on): every kernel of the library is launched with
+// programmatic stream serialization and begins with griddepcontrol.launch_dependents + (after its shared-memory / TMEM
+// prologue) griddepcontrol.wait, so the next kernel's launch latency and prologue overlap the tail of the previous
+// one - ~14 000 kernel boundaries per clip. Correctness does not depend on it: the wait is a full dependency on the
+// previous grid (completion + memory visibility), and without the attribute both instructions are no-ops.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace mimo

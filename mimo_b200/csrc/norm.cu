@@ -51,6 +51,8 @@ template <bool kBf16>
 __global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(GnArgs a) {
   using C = Cvt<kBf16>;
   __shared__ float4 s_red[kGnMaxThreads];  // per-thread (sumA, sqA, sumB, sqB)
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
   const int cv = tid % a.vecs;
@@ -103,6 +105,8 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(GnArgs a) {
   using C = Cvt<kBf16>;
   __shared__ float s_tot[4][128];
   __shared__ float s_mean[64], s_rstd[64];
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
   const int g2 = a.groups * 2;
@@ -218,6 +222,8 @@ layernorm_kernel(const void* __restrict__ x, const void* __restrict__ gamma, con
                  long long rows_per_frame, int frames, int pe_off) {
   using C = Cvt<kBf16>;
   using T = typename C::T;
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -315,6 +321,8 @@ layernorm5_kernel(const void* __restrict__ x, const void* __restrict__ gamma, co
   using T = typename C::T;
   constexpr int R = 32 / L;       // rows per warp pass
   constexpr int Cdim = 40 * L;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int sub = lane % L;
   const int rsel = lane / L;
@@ -405,11 +413,11 @@ static void launch_ln5(int L, const void* x, const void* gamma, const void* beta
   const int rows_per_block = 8 * kLnIter * (32 / L);
   const unsigned blocks = div_up(rows, rows_per_block);
   if (L == 8)
-    layernorm5_kernel<kBf16, 8><<<blocks, 256, 0, st>>>(x, gamma, beta, out, rows, eps, pe, rpf, frames, pe_off);
+    launch_k(layernorm5_kernel<kBf16, 8>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, out, rows, eps, pe, rpf, frames, pe_off);
   else if (L == 16)
-    layernorm5_kernel<kBf16, 16><<<blocks, 256, 0, st>>>(x, gamma, beta, out, rows, eps, pe, rpf, frames, pe_off);
+    launch_k(layernorm5_kernel<kBf16, 16>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, out, rows, eps, pe, rpf, frames, pe_off);
   else
-    layernorm5_kernel<kBf16, 32><<<blocks, 256, 0, st>>>(x, gamma, beta, out, rows, eps, pe, rpf, frames, pe_off);
+    launch_k(layernorm5_kernel<kBf16, 32>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, out, rows, eps, pe, rpf, frames, pe_off);
 }
 
 }  // namespace mimo
@@ -465,14 +473,15 @@ extern "C" int mimo_groupnorm(const mimo_groupnorm_params* p, void* stream) {
   a.silu = p->silu;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(pl.bpi, p->n);
+  cudaError_t e;
   if (p->dtype == MIMO_BF16) {
-    gn_stats_kernel<true><<<grid, pl.threads, 0, st>>>(a);
-    gn_apply_kernel<true><<<grid, pl.threads, 0, st>>>(a);
+    e = launch_k(gn_stats_kernel<true>, grid, dim3(pl.threads), 0, st, a);
+    if (e == cudaSuccess) e = launch_k(gn_apply_kernel<true>, grid, dim3(pl.threads), 0, st, a);
   } else {
-    gn_stats_kernel<false><<<grid, pl.threads, 0, st>>>(a);
-    gn_apply_kernel<false><<<grid, pl.threads, 0, st>>>(a);
+    e = launch_k(gn_stats_kernel<false>, grid, dim3(pl.threads), 0, st, a);
+    if (e == cudaSuccess) e = launch_k(gn_apply_kernel<false>, grid, dim3(pl.threads), 0, st, a);
   }
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("groupnorm launch", e);
   return MIMO_OK;
 }
@@ -499,9 +508,11 @@ extern "C" int mimo_layernorm(const void* x, const void* gamma, const void* beta
   }
   const unsigned blocks = div_up(rows, 8);
   if (dtype == MIMO_BF16)
-    layernorm_kernel<true><<<blocks, 256, 0, st>>>(x, gamma, beta, out, rows, c, eps, pe, rows_per_frame, frames, pe_frame_offset);
+    launch_k(layernorm_kernel<true>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, out, static_cast<long long>(rows), c, eps, pe,
+             static_cast<long long>(rows_per_frame), frames, pe_frame_offset);
   else
-    layernorm_kernel<false><<<blocks, 256, 0, st>>>(x, gamma, beta, out, rows, c, eps, pe, rows_per_frame, frames, pe_frame_offset);
+    launch_k(layernorm_kernel<false>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, out, static_cast<long long>(rows), c, eps, pe,
+             static_cast<long long>(rows_per_frame), frames, pe_frame_offset);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("layernorm launch", e);
   return MIMO_OK;

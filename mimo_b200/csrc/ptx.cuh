@@ -22,6 +22,10 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// programmatic dependent launch (see host_util.h: launch_k)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------

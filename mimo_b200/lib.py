@@ -145,7 +145,7 @@ SYMBOLS = {
     "mimo_cfg_ddim_step": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _I64, _F, _F, _F, _F, _F, _I32, _VP]),
 }
 # test hook, not part of the public header
-_DEBUG_SYMBOLS = {"mimo_debug_splitk": (C.c_int, [C.c_int]), "mimo_debug_force_bn": (C.c_int, [C.c_int]), "mimo_debug_attn_variant": (C.c_int, [C.c_int]),
+_DEBUG_SYMBOLS = {"mimo_debug_pdl": (C.c_int, [C.c_int]), "mimo_debug_splitk": (C.c_int, [C.c_int]), "mimo_debug_force_bn": (C.c_int, [C.c_int]), "mimo_debug_attn_variant": (C.c_int, [C.c_int]),
                   "mimo_debug_attn_trace": (C.c_int, [C.c_void_p]),
                   "mimo_debug_gemm_trace": (C.c_int, [C.c_void_p])}
 
@@ -172,6 +172,8 @@ def load() -> C.CDLL:
         if lib.mimo_abi_sizeof(which) != C.sizeof(st):
             raise MimoError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes in lib.py but "
                             f"{lib.mimo_abi_sizeof(which)} in {LIB_PATH.name}; rebuild the library")
+    if os.environ.get("MIMO_B200_PDL") == "0":  # A/B switch for programmatic dependent launch (default: on)
+        lib.mimo_debug_pdl(0)
     _lib = lib
     return lib
 
