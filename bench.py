@@ -359,6 +359,7 @@ def run_ours(args):
         "e2e": {"value": round(FRAMES / e2e_s, 4), "unit": "frames/s", "h2d_bytes_per_step": pipe.io_bytes["h2d"],
                 "d2h_bytes_per_step": pipe.io_bytes["d2h"], "clips_timed": k_e2e},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "whole_path_frac_of_tensor_peak": round(TFLOP_PER_FRAME * value / (world * measured_peaks()[0]), 4),
         "phases_ms": {k: round(v, 1) for k, v in phases.items()}, "calls_bracketed": calls, "kernels": kernels,
         "kernels_source": kernels_src,
     }
