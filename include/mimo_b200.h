@@ -78,7 +78,8 @@ typedef struct {
   mimo_epilogue ep;
   /* optional scratch (device, 16-byte aligned, contents irrelevant, may be shared by all calls of a stream): lets small-M /
    * long-K problems split the K loop over several CTAs (fp32 partials, summed in a fixed order by a second kernel:
-   * deterministic). NULL = never split. */
+   * deterministic). NULL = never split. (Disabled by default inside the library: measured slower on B200 at the shapes
+   * of this path - see csrc/gemm_tcgen05.cu.) */
   void* workspace;
   int64_t workspace_bytes;
 } mimo_gemm_params;

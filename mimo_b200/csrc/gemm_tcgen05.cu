@@ -768,7 +768,11 @@ static EpiArgs make_epi(const mimo_epilogue& e, int N) {
   return a;
 }
 
-static int g_splitk = 1;  // test hook (mimo_debug_splitk): 0 = never split, 1 = automatic
+// Split-K is OFF by default: measured on B200 (profiles/r02_splitk_bench.log) the second kernel and the fp32 partial
+// traffic cost more than the better SM fill buys at every shape of the path (e.g. conv 6x8x8 1280->1280: 60 us un-split,
+// 136 us with 9 splits; 16x16 level: +-2 %), and an M-dependent summation order would break the bit-identity of sharded
+// and un-sharded runs. mimo_debug_splitk(1) enables the automatic choice (tests/test_kernels_gpu.py keeps it honest).
+static int g_splitk = 0;
 
 static int launch_reduce(int dtype, const float* part, int splits, long long M, int N, const mimo_epilogue& e, void* out,
                          long long ldo, cudaStream_t st) {
