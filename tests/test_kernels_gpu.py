@@ -115,7 +115,7 @@ def test_split_k_small_m_long_k(probe):
     got2 = ops.gemm(a, w, bias=b, rowvec=rv, rows_per_group=192, residual=r, act=L.ACT_SILU)
     lib.mimo_debug_splitk(0)
     plain = ops.gemm(a, w, bias=b, rowvec=rv, rows_per_group=192, residual=r, act=L.ACT_SILU)
-    lib.mimo_debug_splitk(1)
+    lib.mimo_debug_splitk(1)  # on again for the convolution case below
     assert torch.equal(got, got2)
     assert probe.report("split-K gemm 384x1280x5120", got, ref) and probe.report("  vs un-split", got, plain.float(), tol=1e-3)
     # 3x3 convolution, two sources (up-block concat), time-embedding row vector, residual
@@ -133,5 +133,5 @@ def test_split_k_small_m_long_k(probe):
     got = ops.conv3x3(x0, wp, n, h, h, x1=x1, bias=bias, rowvec=tv, rows_per_group=3 * h * h, residual=res)
     lib.mimo_debug_splitk(0)
     plain = ops.conv3x3(x0, wp, n, h, h, x1=x1, bias=bias, rowvec=tv, rows_per_group=3 * h * h, residual=res)
-    lib.mimo_debug_splitk(1)
+    lib.mimo_debug_splitk(0)  # library default
     assert probe.report("split-K conv 6x8x8 2560->1280", got, ref) and probe.report("  vs un-split", got, plain.float(), tol=1e-3)
