@@ -46,7 +46,7 @@ int ensure_device() {
 }
 int num_sms() { return g_num_sms; }
 
-static bool g_pdl = true;
+static bool g_pdl = false;  // measured on one B200 (power-capped): 1775 ms per clip off, 1800 ms on (profiles/r02_pdl_ab.txt)
 bool pdl_enabled() { return g_pdl; }
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;

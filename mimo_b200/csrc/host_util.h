@@ -20,11 +20,13 @@ int encode_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const u
 
 inline unsigned div_up(long long a, long long b) { return static_cast<unsigned>((a + b - 1) / b); }
 
-// Programmatic dependent launch (test hook mimo_debug_pdl, default on): every kernel of the library is launched with
-// programmatic stream serialization and begins with griddepcontrol.launch_dependents + (after its shared-memory / TMEM
-// prologue) griddepcontrol.wait, so the next kernel's launch latency and prologue overlap the tail of the previous
-// one - ~14 000 kernel boundaries per clip. Correctness does not depend on it: the wait is a full dependency on the
-// previous grid (completion + memory visibility), and without the attribute both instructions are no-ops.
+// Programmatic dependent launch (mimo_debug_pdl / MIMO_B200_PDL=1; default OFF): every kernel of the library can be
+// launched with programmatic stream serialization; it begins with griddepcontrol.launch_dependents and, after its
+// shared-memory / TMEM prologue, griddepcontrol.wait, so the next kernel's launch latency and prologue overlap the tail
+// of the previous one (~14 000 kernel boundaries per clip). Correctness does not depend on it: the wait is a full
+// dependency on the previous grid (completion + memory visibility); without the attribute both instructions are no-ops.
+// Measured on one power-capped B200 it did not pay: 1800 ms per clip with it, 1775 ms without (the SM clock under the
+// 1 kW cap drops by the same 1.3 % the removed gaps would have gained) - kept as a switch for launch-bound regimes.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

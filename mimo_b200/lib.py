@@ -172,8 +172,8 @@ def load() -> C.CDLL:
         if lib.mimo_abi_sizeof(which) != C.sizeof(st):
             raise MimoError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes in lib.py but "
                             f"{lib.mimo_abi_sizeof(which)} in {LIB_PATH.name}; rebuild the library")
-    if os.environ.get("MIMO_B200_PDL") == "0":  # A/B switch for programmatic dependent launch (default: on)
-        lib.mimo_debug_pdl(0)
+    if os.environ.get("MIMO_B200_PDL") in ("0", "1"):  # A/B switch for programmatic dependent launch (default: off)
+        lib.mimo_debug_pdl(int(os.environ["MIMO_B200_PDL"]))
     _lib = lib
     return lib
 
