@@ -442,9 +442,11 @@ class UNetEngine:
         if b != len(st["branches"]):
             raise L.MimoError(f"forward() got a batch of {b} but this engine evaluates branches {st['branches']}")
         # unconditional rows ignore the bank (mutual_self_attention.py:177-197); conditional rows read bank 1
-        idx = sum(([-1 if br == 0 else 1] * frames for br in st["branches"]), []) if st["cfg"] else [0] * (b * frames)
+        nbank = next(iter(st["banks"].values())).shape[0] if st["banks"] else 1
+        cond = nbank - 1  # banks of both CFG halves: the conditional one is the second; conditional half only: the first
+        idx = sum(([-1 if br == 0 else cond] * frames for br in st["branches"]), []) if st["cfg"] else [0] * (b * frames)
         new = torch.tensor(idx, dtype=torch.int32, device=self.device)
-        st["bank_index"] = self._store(f"bank_index_{len(idx)}_{st['branches']}", {"i": new})["i"]
+        st["bank_index"] = self._store(f"bank_index_{len(idx)}_{st['branches']}_{cond}", {"i": new})["i"]
         st["n_bank_frames"] = sum(1 for i in idx if i >= 0)
         st["frames"] = frames
 

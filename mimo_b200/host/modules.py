@@ -345,7 +345,13 @@ class ReferenceAttentionControl:
             raise MimoError("update() before the reference UNet's forward pass")
         latents, ehs = pending
         den, ref = self.unet.engine(), writer.unet.engine()
-        banks = ref.write_banks(latents, ehs, den)
+        if self.cfg and latents.shape[0] == 2:
+            # Only the conditional half of the reference pass is ever read: unconditional rows of the denoising UNet
+            # skip the bank (mutual_self_attention.py:177-197), so the writer's unconditional half (which the reference
+            # computes and stores, :137-147) is dead work here - the engine runs the conditional row alone.
+            banks = ref.write_banks(latents[1:2].contiguous(), ehs[1:2].contiguous(), den)
+        else:
+            banks = ref.write_banks(latents, ehs, den)
         den.begin_clip(ehs, banks, cfg=self.cfg, frames=1, branches=getattr(self.unet, "_branches", None))
         self.unet._xattn_key = None
 

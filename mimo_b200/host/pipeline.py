@@ -262,10 +262,18 @@ class Pose2VideoPipeline:
         ref_px = uint8_to_tensor(inp["ref_u8"], True).to(dtype)
         bk_px = uint8_to_tensor(inp["bk_unique_u8"], True).to(dtype)
         pose_px = uint8_to_tensor(inp["pose_u8"], False).permute(1, 0, 2, 3).unsqueeze(0).to(dtype)  # [1, 3, F, H, W]
-        ref_latents = enc.encode_mean(ref_px) * 0.18215  # :424-431
         rank, world, group = self._shard
         n_bk = bk_px.shape[0]
-        if world > 1 and n_bk >= world:
+        if not (world > 1 and n_bk >= world) and n_bk <= 4:
+            # animate mode: the reference image and the (deduplicated) background go through the encoder together
+            # (per-image arithmetic: the same values as two calls, one kernel chain instead of two)
+            both = enc.encode_mean(torch.cat([ref_px, bk_px]))
+            ref_latents, bk_mean = both[:1] * 0.18215, both[1:]
+        else:
+            ref_latents, bk_mean = enc.encode_mean(ref_px) * 0.18215, None  # :424-431
+        if bk_mean is not None:
+            pass
+        elif world > 1 and n_bk >= world:
             # edit mode: one distinct background per frame (run_edit.py:232-238) - every GPU encodes its share, one
             # all-gather per clip (per-image arithmetic: identical to encoding them all here)
             import torch.distributed as dist

@@ -81,7 +81,10 @@ def _oracle_engines(monkeypatch, O, cfg, vcfg):
             b, c, f, h, w = sample.shape
             pose = pose_nhwc.reshape(b, f, h, w, -1).permute(0, 4, 1, 2, 3)
             st = self.clip_state
-            return O.denoising_unet(self.sd, sample, int(timestep), st["ehs"], pose, st["banks"], cfg, cfg=st["cfg"])
+            # the host layer hands over the conditional half of the banks only (the unconditional half is never read);
+            # the oracle restates the reference, which keeps both: fill the unused slot with a copy
+            banks = {k: (v if v.shape[0] == b else v.repeat(b, 1, 1)) for k, v in st["banks"].items()}
+            return O.denoising_unet(self.sd, sample, int(timestep), st["ehs"], pose, banks, cfg, cfg=st["cfg"])
 
     class Ref:
         def __init__(self, sd):
