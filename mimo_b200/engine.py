@@ -89,6 +89,17 @@ class _Packer:
         return ops.pack_conv_up2x_weight(self.t(p + ".weight")), self.t(p + ".bias")
 
 
+def bank_index_rows(branches: Sequence[int], frames: int, cfg: bool, nbank: int):
+    """Bank routing of every frame-sample row of a forward (mutual_self_attention.py:154-197): -1 = attend to self only
+    (the unconditional CFG branch), else the index of the bank feature map to append. With CFG the conditional bank is the
+    LAST of the `nbank` maps the writer handed over (both halves -> index 1; conditional half only -> index 0); without
+    CFG every row reads bank 0. Returns (indices, index of the conditional bank)."""
+    cond = nbank - 1
+    if not cfg:
+        return [0] * (len(branches) * frames), cond
+    return sum(([-1 if br == 0 else cond] * frames for br in branches), []), cond
+
+
 class UNetEngine:
     """Executes the denoising UNet3D (motion=True) or the reference UNet2D bank pass (motion=False)."""
 
@@ -443,8 +454,7 @@ class UNetEngine:
             raise L.MimoError(f"forward() got a batch of {b} but this engine evaluates branches {st['branches']}")
         # unconditional rows ignore the bank (mutual_self_attention.py:177-197); conditional rows read bank 1
         nbank = next(iter(st["banks"].values())).shape[0] if st["banks"] else 1
-        cond = nbank - 1  # banks of both CFG halves: the conditional one is the second; conditional half only: the first
-        idx = sum(([-1 if br == 0 else cond] * frames for br in st["branches"]), []) if st["cfg"] else [0] * (b * frames)
+        idx, cond = bank_index_rows(st["branches"], frames, st["cfg"], nbank)
         new = torch.tensor(idx, dtype=torch.int32, device=self.device)
         st["bank_index"] = self._store(f"bank_index_{len(idx)}_{st['branches']}_{cond}", {"i": new})["i"]
         st["n_bank_frames"] = sum(1 for i in idx if i >= 0)

@@ -210,3 +210,14 @@ def test_packed_weight_cache_container_round_trip(tmp_path):
     b["k"][5000] += 1  # a change between the sampled positions is caught only by the full hash
     assert WC.fingerprint(a) == WC.fingerprint({"k": torch.arange(10000.0)})
     assert WC.fingerprint(a, "x") != WC.fingerprint(a, "y")
+
+
+def test_bank_routing_rows():
+    """Which bank each frame-sample row reads (engine.bank_index_rows): unconditional rows never read the bank, the
+    conditional bank is the last map the writer handed over, a CFG-sharded GPU holds one branch only."""
+    from mimo_b200.engine import bank_index_rows
+    assert bank_index_rows((0, 1), 3, True, 2) == ([-1, -1, -1, 1, 1, 1], 1)      # both halves written (direct engine use)
+    assert bank_index_rows((0, 1), 2, True, 1) == ([-1, -1, 0, 0], 0)             # conditional half only (the pipeline)
+    assert bank_index_rows((1,), 2, True, 1) == ([0, 0], 0)                       # CFG-sharded, conditional GPU
+    assert bank_index_rows((0,), 2, True, 1) == ([-1, -1], 0)                     # CFG-sharded, unconditional GPU
+    assert bank_index_rows((0,), 4, False, 1) == ([0, 0, 0, 0], 0)                # guidance <= 1: every row reads bank 0
