@@ -116,17 +116,24 @@ class Pose2VideoPipeline:
 
     enable_frame_sharding = enable_sharding  # round-1 name
 
+    def release_exchanges(self):
+        """Collective (every rank calls it): unmap and free the peer buffers of exchanges that were replaced because the
+        clip geometry or the partitioning changed. The exchanges in use stay."""
+        _, _, group = self._shard
+        for x in self.__dict__.pop("_xchg_retired", []):
+            x.destroy(group)
+
     def _exchanges(self, plan, nb: int, n_my_windows: int, fl: int, h: int, w: int, dtype):
         """(frame-group exchange or None, world exchange): peer buffers sized for this geometry; collective."""
         from .shard import Exchange
         rank, world, group = self._shard
         key = (plan, nb, n_my_windows, fl, h, w, dtype)
         if getattr(self, "_xchg_key", None) != key:
-            # captured forwards hold the old buffers' addresses: drop them before the buffers go away
+            # captured forwards hold the old buffers' addresses: drop the graphs; the old exchanges are retired, not
+            # freed (freeing peer-mapped memory is a collective: release_exchanges() does it when the caller wants to)
             self.denoising_unet.engine()._graphs.clear()
-            for old in (getattr(self, "_xchg_frame", None), getattr(self, "_xchg_world", None)):
-                if old is not None:
-                    old.destroy(group)
+            retired = self.__dict__.setdefault("_xchg_retired", [])
+            retired += [x for x in (getattr(self, "_xchg_frame", None), getattr(self, "_xchg_world", None)) if x is not None]
             self._xchg_frame = self._xchg_world = None
             esz = torch.empty((), dtype=dtype).element_size()
             c0 = self.denoising_unet.config.block_out_channels[0]

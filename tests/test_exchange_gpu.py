@@ -82,7 +82,8 @@ def test_sharded_clip_equals_single_gpu(world, tmp_path):
     out = tmp_path / "mgpu.json"
     port = 29600 + (os.getpid() + world) % 300
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), str(ROOT / "scripts" / "mgpu_check.py"), "--out", str(out)]
+           "127.0.0.1", "--master-port", str(port), str(ROOT / "scripts" / "mgpu_check.py"), "--out", str(out),
+           "--frames", "24", "48"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, "sharded clip differs from the single-GPU clip (see stdout)"
