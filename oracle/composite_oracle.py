@@ -1,7 +1,9 @@
 """TEST INFRASTRUCTURE (never imported by mimo_b200/): numpy restatement of run_edit.py's per-frame scene compositing
 (/root/reference/run_edit.py:282-300) — the blend chain after the generated frame has been resized, un-padded and pasted
-on the white canvas. Parity unpinned by the reference's own code (the loop lives inside MIMO.run, behind TensorFlow /
-model loading at import time); it is restated line by line, with numpy's own type promotion doing the arithmetic:
+on the white canvas. The loop lives inside MIMO.run, behind TensorFlow / model loading at import time, so it cannot be
+imported; it is restated line by line, with numpy's own type promotion doing the arithmetic, and PINNED against the
+reference's own statements: tests/test_dropin_cpu.py extracts the loop from run_edit.py by AST, executes it with
+tools/util.py's get_mask on a synthetic clip and requires byte-identical frames from host/composite.py + this oracle:
 
     res_image = res_image * mask_full[:, :, np.newaxis] + bk_image * (1 - mask_full[:, :, np.newaxis])      :284
     occ_mask = occ_mask / 255.0;  res_image = res_image * (1 - occ) + vid_image * occ                       :288-292

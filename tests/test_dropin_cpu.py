@@ -264,3 +264,75 @@ def test_run_animate_model_construction_block(compat_path, tmp_path):
     from mimo_b200.lib import MimoError
     with pytest.raises(MimoError):
         pipe.pose_guider(torch.zeros(1, 3, 1, 64, 64, dtype=torch.float16))
+
+
+def test_scene_compositing_matches_the_reference_loop(compat_path, monkeypatch):
+    """run_edit.py's post-processing loop (:253-304), executed from the reference file with tools/util.py's own get_mask,
+    against mimo_b200.host.composite.composite_clip on the same synthetic clip. The blend kernel needs a GPU, so here (and
+    only here) ops.composite_frame is the numpy oracle: this pins the helper's host logic (PIL resize / crop / paste,
+    INTER_AREA mask resize, mask placement, cross-fade factor, 16-way mask choice) AND the oracle's arithmetic to the
+    reference's code; the kernel is pinned to the oracle bit for bit on the GPU (tests/test_clip_composite_gpu.py)."""
+    import cv2
+    from PIL import Image
+
+    from mimo_b200 import ops
+    from mimo_b200.host import composite
+    from oracle.composite_oracle import composite_frame
+    spec = importlib.util.spec_from_file_location("_reference_tools_util", REF / "tools" / "util.py")
+    ref_util = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_util)
+
+    rng = np.random.RandomState(3)
+    W, H, n_frames, overlay = 96, 72, 7, 2
+    contexts = [[0, 1, 2, 3, 4], [3, 4, 5, 6]]  # frames 3, 4 are composited twice: cross-fade
+    bboxes = [(0, 60, 4, 72), (20, 96, 0, 50)]   # touch different borders: different feather masks
+    bk = [Image.fromarray(rng.randint(0, 256, (H, W, 3), dtype=np.uint8)) for _ in range(n_frames)]
+    vid = [Image.fromarray(rng.randint(0, 256, (H, W, 3), dtype=np.uint8)) for _ in range(n_frames)]
+    occ = [Image.fromarray(np.repeat(rng.randint(0, 256, (H, W, 1), dtype=np.uint8), 3, axis=2)) for _ in range(n_frames)]
+    mask_list = [rng.rand(64, 64).astype(np.float32) for _ in range(16)]
+    pads, padvs = [], []
+    for k, ctx in enumerate(contexts):
+        w_min, w_max, h_min, h_max = bboxes[k]
+        bw, bh = w_max - w_min, h_max - h_min
+        side = max(bw, bh)
+        side += (16 - side % 16) % 16
+        top = (side - bh) // 2
+        left = (side - bw) // 2
+        for _ in ctx:
+            pads.append([side, side])
+            padvs.append([top, side - bh - top, left, side - bw - left])
+    video = torch.rand(3, sum(len(c) for c in contexts), 64, 64)
+
+    # ---- the reference's loop, verbatim from run_edit.py ----
+    tree = ast.parse((REF / "run_edit.py").read_text())
+    run = next(f for c in tree.body if isinstance(c, ast.ClassDef) and c.name == "MIMO"
+               for f in c.body if isinstance(f, ast.FunctionDef) and f.name == "run")
+    loop = next(st for st in run.body if isinstance(st, ast.For) and isinstance(st.iter, ast.Call)
+                and getattr(st.iter.func, "id", "") == "enumerate" and getattr(st.iter.args[0], "id", "") == "context_list")
+    init = next(st for st in run.body if isinstance(st, ast.Assign) and getattr(st.targets[0], "id", "") == "res_images")
+    idx0 = next(st for st in run.body if isinstance(st, ast.Assign) and getattr(st.targets[0], "id", "") == "video_idx")
+    mod = ast.Module(body=[idx0, init, loop], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    me = SimpleNamespace(args=SimpleNamespace(L=n_frames), mask_list=mask_list)
+    ns = dict(np=np, cv2=cv2, Image=Image, get_mask=ref_util.get_mask, self=me, context_list=contexts,
+              bbox_clip_list=bboxes, bk_images_ori=bk, vid_images_ori=vid, occ_mask_images=occ,
+              clip_pad_list_context=pads, clip_padv_list_context=padvs, video=video, overlay=overlay)
+    exec(compile(mod, "run_edit.py:MIMO.run[post-process]", "exec"), ns)
+    want = ns["res_images"]
+
+    # ---- this repo's helper, with the blend evaluated by the oracle instead of the kernel ----
+    def blend_on_cpu(canvas, bkf, mask, *, occ=None, vid=None, prev=None, factor=0.0, out=None):
+        f = lambda t: None if t is None else t.cpu().numpy()
+        return torch.from_numpy(composite_frame(f(canvas), f(bkf), f(mask), f(occ), f(vid), f(prev), factor))
+
+    monkeypatch.setattr(ops, "composite_frame", blend_on_cpu)
+    got = composite.composite_clip(video, contexts, bboxes, bk, vid, occ, pads, padvs, mask_list, n_frames, overlay, device="cpu")
+    for i in range(n_frames):
+        assert want[i] is not None and got[i] is not None
+        assert np.array_equal(want[i], got[i]), (i, int((want[i].astype(int) - got[i].astype(int)).__abs__().max()))
+    # and without an occlusion mask (animate-style templates, run_edit.py:262-265)
+    ns.update(occ_mask_images=None)
+    exec(compile(mod, "run_edit.py:MIMO.run[post-process]", "exec"), ns)
+    got = composite.composite_clip(video, contexts, bboxes, bk, vid, None, pads, padvs, mask_list, n_frames, overlay, device="cpu")
+    for i in range(n_frames):
+        assert np.array_equal(ns["res_images"][i], got[i]), i
