@@ -7,7 +7,7 @@ The engine must be at least as close to the fp32 oracle as the reference's own e
 
     rel_l2(engine, oracle_fp32)  <=  max(1e-3, rel_l2(torch_fp16 execution of the same graph, oracle_fp32))
 
-Every test prints the three numbers; scripts/collect_parity.py copies them into profiles/.
+Every test prints its numbers and the module writes them to gpurun_out/parity_errors.json (copied to profiles/).
 Also here: determinism (bit-identical repeats), the VAE encoder / decoder at full size, bf16, and the golden clip the
 reference's own pipeline wrote (tests/golden/pipeline_cfg1.pt, oracle/pin_against_reference.py)."""
 import json
@@ -111,7 +111,7 @@ def test_unet_forward_bf16():
     assert e_eng <= max(8e-3, e_ref), (e_eng, e_ref)  # bf16 keeps 8 mantissa bits: 8x the fp16 unit roundoff
 
 
-def test_groupnorm_is_deterministic_and_one_pass_exact():
+def test_groupnorm_is_deterministic_and_exact():
     from mimo_b200 import ops
     torch.manual_seed(3)
     for n, hw, c0, c1, silu in [(48, 4096, 320, 0, True), (6, 1024, 640, 320, True), (3, 64, 1280, 1280, False),
