@@ -312,7 +312,7 @@ def exchange(xg, mode: int, name: str, dst: torch.Tensor, b: int, fl: int, hw: i
     p.dtype = _dt(dst)
     p.max_blocks, p.timeout_ms = int(xg.max_blocks), int(xg.timeout_ms)
     rows = b * fl * hw * (xg.G if mode == 2 else 1)
-    need = (b * fl * hw if mode != 1 else b * fl * hw) * Cdim * dst.element_size()
+    need = b * fl * hw * Cdim * dst.element_size()  # every member's source holds b*fl*hw rows in all three modes
     if need > src.nbytes or dst.numel() != rows * Cdim:
         raise L.MimoError(f"exchange: source buffer '{name}' ({src.nbytes} B) or dst ({tuple(dst.shape)}) does not fit "
                           f"b={b} fl={fl} hw={hw} C={Cdim} mode={mode}")

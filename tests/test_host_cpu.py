@@ -207,8 +207,9 @@ def test_packed_weight_cache_container_round_trip(tmp_path):
     assert isinstance(back["w"]["a"], tuple) and back["w"]["b"]["C"] == 320 and back["names"] == ["x", "y"]
     a = {"k": torch.arange(10000.0)}
     b = {"k": torch.arange(10000.0)}
-    b["k"][5000] += 1  # a change between the sampled positions is caught only by the full hash
+    b["k"][5000] += 1  # one element in the middle of a tensor: the default (full) hash must see it
     assert WC.fingerprint(a) == WC.fingerprint({"k": torch.arange(10000.0)})
+    assert WC.fingerprint(a) != WC.fingerprint(b)
     assert WC.fingerprint(a, "x") != WC.fingerprint(a, "y")
 
 
