@@ -298,4 +298,6 @@ def test_golden_clip_written_by_the_reference_pipeline(golden_dir):
     ve = _rel(res["videos"].cpu()[:, :, :, ::8, ::8], g["videos"])
     RESULTS["golden_pipeline_cfg1"] = {"latents": le, "videos_subsampled": ve}
     print(f"golden clip (reference pipeline, fp32 CPU): latents {le:.3e} videos {ve:.3e}")
-    assert le < 3e-3 and ve < 3e-3
+    # measured 2.7e-3 / 8.9e-4 (profiles/r02_parity_errors_run2.json); the same two-step amplification of the per-forward
+    # fp16 error as in the 512x512 clip above, where PyTorch-fp16 itself sits at 3.3e-3 / 1.1e-3 from the fp32 oracle
+    assert le < 4e-3 and ve < 2e-3
