@@ -71,6 +71,71 @@ def _dedupe_images(images) -> "tuple[list, torch.Tensor]":
     return first, torch.tensor(inverse, dtype=torch.long)
 
 
+_POOL = None
+
+
+def _pool():
+    """Host threads for the pre-processing: PIL's resize / convert and torch's CPU random draw release the GIL."""
+    global _POOL
+    import os
+    if _POOL is None or _POOL[0] != os.getpid():  # a forked child inherits the object but not its threads
+        from concurrent.futures import ThreadPoolExecutor
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        _POOL = (os.getpid(), ThreadPoolExecutor(max_workers=max(2, min(8, n)), thread_name_prefix="mimo-pre"))
+    return _POOL[1]
+
+
+def _sample_key(im, raw: bytes):
+    """Bucket key of an image for the dedupe: geometry + CRC-32 of every 1021st byte (a prime stride visits every
+    channel and column phase). Only a bucket: equality is always confirmed on the full bytes."""
+    import zlib
+    return (im.size, im.mode, len(raw), zlib.crc32(raw[::1021]))
+
+
+def stage_frames_u8(images, height: int, width: int, pinned: bool, scale_factor: int = 8, raws=None) -> torch.Tensor:
+    """pil_to_uint8() written straight into one (pinned) staging tensor [N, h, w, 3]: the same pixel values — PIL's
+    `convert("RGB")` and `resize` return plain copies when the mode / size already match (Image.py: `return self.copy()`),
+    so those two copies, the per-image ndarray and the np.stack + pin_memory copies of the simple version are skipped,
+    and frames that do need the LANCZOS resize run on the host thread pool (PIL releases the GIL inside it).
+    `raws[i]`, when given, is `images[i].tobytes()` (the dedupe already made it)."""
+    imgs = images if isinstance(images, (list, tuple)) else [images]
+    w, h = width - width % scale_factor, height - height % scale_factor
+    out = torch.empty((len(imgs), h, w, 3), dtype=torch.uint8, pin_memory=pinned)
+    dst = out.numpy().reshape(len(imgs), -1)
+
+    def one(i):
+        im = imgs[i]
+        if im.mode == "RGB" and im.size == (w, h):
+            raw = raws[i] if raws is not None else im.tobytes()
+        else:
+            raw = im.convert("RGB").resize((w, h), resample=PIL.Image.LANCZOS).tobytes()
+        dst[i] = np.frombuffer(raw, dtype=np.uint8)
+
+    heavy = [i for i, im in enumerate(imgs) if im.size != (w, h)]
+    if len(heavy) > 1:
+        list(_pool().map(one, range(len(imgs))))
+    else:
+        for i in range(len(imgs)):
+            one(i)
+    return out
+
+
+def _dedupe_raws(images) -> "tuple[list, torch.Tensor, list]":
+    """_dedupe_images() with a sampled bucket key, also returning the pixel bytes of the representatives."""
+    first, inverse, buckets, raws = [], [], {}, []
+    for i, im in enumerate(images):
+        raw = im.tobytes()
+        key = _sample_key(im, raw)
+        j = next((k for k in buckets.get(key, ()) if raws[k] == raw), None)
+        if j is None:
+            j = len(first)
+            buckets.setdefault(key, []).append(j)
+            first.append(i)
+            raws.append(raw)
+        inverse.append(j)
+    return first, torch.tensor(inverse, dtype=torch.long), raws
+
+
 def _randn_tensor(shape, generator, device: torch.device, dtype) -> torch.Tensor:
     """diffusers.utils.torch_utils.randn_tensor [3P] (pipeline :175-177): the draw happens on the generator's device
     (CPU generator -> CPU draw in the target dtype, then moved: this is what defines seed parity); a list of
@@ -219,20 +284,29 @@ class Pose2VideoPipeline:
                    dtype) -> Dict[str, torch.Tensor]:
         """Host side of __call__: PIL -> pinned CPU tensors (what the reference does at pipeline :379-381, :409-418,
         :424-426, :435-437, :446-453 before anything touches the device)."""
-        pin = lambda t: t.contiguous().pin_memory() if torch.cuda.is_available() else t.contiguous()
+        pinned = torch.cuda.is_available()
+        pin = lambda t: t.contiguous().pin_memory() if pinned else t.contiguous()
         bks = list(vid_bk_images)
         if len(bks) != video_length or len(pose_images) != video_length:
             raise ValueError(f"video_length={video_length} but {len(pose_images)} pose images and {len(bks)} background "
                              "images were passed (pipeline :435-453 indexes both per frame)")
-        first, inverse = _dedupe_images(bks)  # identical background frames are converted, copied and encoded once
-        return {
-            "clip_pixels": pin(self._clip_pixels(ref_image)),
-            "ref_u8": pin(pil_to_uint8(ref_image, height, width)),
-            "bk_unique_u8": pin(pil_to_uint8([bks[i] for i in first], height, width)),
-            "bk_inverse": inverse,
-            "pose_u8": pin(pil_to_uint8(list(pose_images), height, width)),  # [F, H, W, 3]
-            "latents": pin(self.prepare_latents(1, 4, width, height, video_length, dtype, "cpu", generator)),
-        }
+        # the noise draw (CPU generator, target dtype: ~10 ms of one core for a 24-frame clip) runs beside the image staging
+        noise = _pool().submit(self.prepare_latents, 1, 4, width, height, video_length, dtype, "cpu", generator)
+        try:
+            # identical background frames are converted, copied and encoded once; every frame is written straight into
+            # its pinned staging tensor (stage_frames_u8: same bytes as pil_to_uint8, without the intermediate copies)
+            first, inverse, raws = _dedupe_raws(bks)
+            out = {
+                "clip_pixels": pin(self._clip_pixels(ref_image)),
+                "ref_u8": stage_frames_u8(ref_image, height, width, pinned),
+                "bk_unique_u8": stage_frames_u8([bks[i] for i in first], height, width, pinned, raws=raws),
+                "bk_inverse": inverse,
+                "pose_u8": stage_frames_u8(list(pose_images), height, width, pinned),  # [F, H, W, 3]
+            }
+        finally:
+            latents = noise.result()  # also on an error above: the generator must not be left in use by a worker
+        out["latents"] = pin(latents)
+        return out
 
     @torch.no_grad()
     def sample_tensors(self, inp: Dict[str, torch.Tensor], num_inference_steps: int, guidance_scale: float,

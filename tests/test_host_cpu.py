@@ -121,6 +121,53 @@ def test_identical_background_frames_are_deduplicated():
     assert first == [0] and inverse.tolist() == [0]
 
 
+def test_staged_preprocess_equals_the_simple_functions():
+    """Pose2VideoPipeline.preprocess() writes frames straight into staging tensors, resizes on host threads, buckets the
+    dedupe by a sampled CRC and draws the noise on a worker thread: every output must equal what the plain functions
+    (pil_to_uint8, _dedupe_images, prepare_latents on the calling thread) give, for frames that need nothing, a mode
+    conversion, a LANCZOS resize, or both."""
+    import numpy as np
+    import PIL.Image
+
+    from mimo_b200.host import pipeline as P
+    from mimo_b200.host.scheduler import DDIMScheduler
+    rng = np.random.RandomState(5)
+    rgb = lambda hh, ww: PIL.Image.fromarray(rng.randint(0, 256, (hh, ww, 3), dtype=np.uint8))
+    F_, size = 6, 64
+    white = lambda: PIL.Image.fromarray(np.full((size, size, 3), 255, np.uint8))
+    near_white = np.full((size, size, 3), 255, np.uint8)
+    near_white[17, 23, 1] = 254  # one byte off, at an offset the 1021-byte sampling stride does not visit
+    assert (17 * size * 3 + 23 * 3 + 1) % 1021 != 0
+    cases = {
+        "as_is": ([rgb(size, size) for _ in range(F_)], [white() for _ in range(F_)]),
+        "resize": ([rgb(90, 70) for _ in range(F_)], [rgb(size, size), white(), white(), rgb(size, size), white(),
+                                                      PIL.Image.fromarray(near_white)]),
+        "modes": ([rgb(size, size).convert("L"), rgb(size, size).convert("RGBA"), rgb(100, 50).convert("L")] +
+                  [rgb(size, size) for _ in range(3)], [rgb(80, 80).convert("RGBA") for _ in range(F_)]),
+    }
+    pipe = P.Pose2VideoPipeline.__new__(P.Pose2VideoPipeline)
+    pipe.scheduler, pipe.vae_scale_factor = DDIMScheduler(prediction_type="v_prediction", clip_sample=False), 8
+    pipe._clip_pixels = lambda im: torch.zeros(1, 3, 2, 2)  # transformers' processor is not under test here
+    for name, (poses, bks) in cases.items():
+        for target in (size, 61):  # 61 -> floored to 56: every frame is resized
+            ref = rgb(size, size)
+            for dtype in (torch.float16, torch.float32):
+                got = pipe.preprocess(ref, poses, bks, target, target, F_, torch.Generator().manual_seed(9), dtype)
+                first, inverse = P._dedupe_images(bks)
+                assert torch.equal(got["bk_inverse"], inverse), name
+                assert torch.equal(got["ref_u8"], P.pil_to_uint8(ref, target, target)), name
+                assert torch.equal(got["pose_u8"], P.pil_to_uint8(poses, target, target)), name
+                assert torch.equal(got["bk_unique_u8"], P.pil_to_uint8([bks[i] for i in first], target, target)), name
+                want = pipe.prepare_latents(1, 4, target, target, F_, dtype, "cpu", torch.Generator().manual_seed(9))
+                assert got["latents"].dtype == dtype and torch.equal(got["latents"], want), name
+    assert P._dedupe_raws(cases["resize"][1])[0] == [0, 1, 3, 5]  # the near-white frame is its own representative
+    with pytest.raises(ValueError):
+        pipe.preprocess(ref, poses[:-1], bks, size, size, F_, torch.Generator().manual_seed(9), torch.float16)
+    # a failing noise draw (generator list of the wrong length) surfaces as the reference's ValueError
+    with pytest.raises(ValueError, match="list of generators"):
+        pipe.preprocess(ref, poses, bks, size, size, F_, [torch.Generator(), torch.Generator()], torch.float16)
+
+
 def test_weight_packers_lay_out_what_the_kernels_index():
     """Host-side packing only (no device): conv weights become [cout, 9 * cin] with K = (ky*3+kx) * cin + ch (the order
     the implicit-GEMM producer walks taps and channel blocks in), GEGLU projections interleave value / gate rows per
