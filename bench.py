@@ -228,7 +228,12 @@ def run_ours(args):
     value = FRAMES / (ms_per_step / 1e3)
 
     # ---- end to end through the public API (PIL in, CPU tensor out) -------------------------------------
-    pipe(ref_img, poses, bks, WIDTH, HEIGHT, FRAMES, DDIM_STEPS, GUIDANCE, generator=clip_seed(99))  # warm the host path
+    # warm the host path: two untimed calls whose results are both alive, as `res` and the clip being produced are in the
+    # timed loop below, so the pinned-memory cache holds the two result buffers before timing starts
+    warm = [pipe(ref_img, poses, bks, WIDTH, HEIGHT, FRAMES, DDIM_STEPS, GUIDANCE, generator=clip_seed(98 + i))
+            for i in range(2)]
+    res = warm.pop()
+    del warm
     sync()
     k_e2e = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
