@@ -37,3 +37,14 @@ def get_context_scheduler(name: str) -> Callable:
     if name == "uniform":
         return uniform
     raise ValueError(f"Unknown context_overlap policy {name}")
+
+
+def get_total_steps(scheduler, timesteps: List[int], num_steps: Optional[int] = None, num_frames: int = ...,
+                    context_size: Optional[int] = None, context_stride: int = 3, context_overlap: int = 4,
+                    closed_loop: bool = True) -> int:
+    """Number of windows over a whole sampling run (src/pipelines/context.py:52-75): the scheduler is evaluated at step
+    index i for every timestep; like the reference, `closed_loop` is accepted but not forwarded."""
+    total = 0
+    for i in range(len(timesteps)):
+        total += sum(1 for _ in scheduler(i, num_steps, num_frames, context_size, context_stride, context_overlap))
+    return total

@@ -269,3 +269,27 @@ def test_bank_routing_rows():
     assert bank_index_rows((1,), 2, True, 1) == ([0, 0], 0)                       # CFG-sharded, conditional GPU
     assert bank_index_rows((0,), 2, True, 1) == ([-1, -1], 0)                     # CFG-sharded, unconditional GPU
     assert bank_index_rows((0,), 4, False, 1) == ([0, 0, 0, 0], 0)                # guidance <= 1: every row reads bank 0
+
+
+def test_context_windows_sweep_against_the_reference_generated_fixture(golden_dir):
+    """tests/golden/context_sweep.json was written by oracle/gen_context_golden.py from the reference's own
+    src/pipelines/context.py: 2 600 (step, frames, size, stride, overlap, closed_loop) cases as window count + CRC-32 of
+    the JSON text, 16 full window lists, ordered_halving fractions and get_total_steps - pure integer logic, bit-exact."""
+    import zlib
+    g = json.loads((golden_dir / "context_sweep.json").read_text())
+    assert len(g["cases"]) >= 2000
+    for step, frames, size, stride, overlap, closed, n, crc in g["cases"]:
+        w = list(context.uniform(step, 20, frames, size, stride, overlap, bool(closed)))
+        assert len(w) == n and zlib.crc32(json.dumps(w, separators=(",", ":")).encode()) == crc, \
+            (step, frames, size, stride, overlap, closed)
+        assert O.uniform_windows(step, frames, size, stride, overlap, bool(closed)) == w  # the oracle's restatement too
+    for key, want in g["full"].items():
+        step, frames, size, stride, overlap, closed = map(int, key.split(","))
+        assert list(context.uniform(step, 20, frames, size, stride, overlap, bool(closed))) == want, key
+    for v, want in g["ordered_halving"].items():
+        assert context.ordered_halving(int(v)) == want
+    sched = context.get_context_scheduler("uniform")
+    for n, frames, size, stride, overlap, want in g["total_steps"]:
+        assert context.get_total_steps(sched, list(range(n)), 20, frames, size, stride, overlap) == want
+    import src.pipelines.context as overlay  # the reference's import path resolves to the same functions
+    assert overlay.get_total_steps is context.get_total_steps and overlay.uniform is context.uniform
