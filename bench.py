@@ -249,106 +249,118 @@ def run_ours(args):
 
     roofline, calls, kernels, kernels_src = None, None, None, "skipped (--no-breakdown)"
     if not args.no_breakdown:
-        # ---- roofline of the dominant kernel: one extra, untimed clip with CUDA-event brackets around every C-ABI call ----
-        # The brackets must time kernels, not the host: each forward is preceded by a ~40 ms device-side spin so that the
-        # host runs ahead and the ~1 400 launches of the forward sit back to back in the stream when they execute.
-        # (Brackets are exact for long kernels - the GEMM / conv / attention families; they over-read the ~10 us kernels by
-        # launch latency, which is why the per-kernel table below comes from CUPTI on a graph-replay clip instead.)
-        den_eng = pipe.denoising_unet.engine()
-        orig_impl = den_eng._forward_impl
-
-        def queued_impl(*a):
-            torch.cuda._sleep(80_000_000)
-            return orig_impl(*a)
-
-        den_eng._forward_impl = queued_impl
-        ops.PROFILE = []
-        pipe.sample_tensors(dev_in, DDIM_STEPS, GUIDANCE)
-        torch.cuda.synchronize()
-        prof, ops.PROFILE = ops.PROFILE, None
-        den_eng._forward_impl = orig_impl
-        if args.dump_calls and rank == 0:
-            with open(args.dump_calls, "w") as fcsv:
-                fcsv.write("idx,name,flops,bytes,ms\n")
-                for i, (name, fl, by, a, b) in enumerate(prof):
-                    fcsv.write(f"{i},{name},{fl:.0f},{by:.0f},{a.elapsed_time(b):.4f}\n")
-        agg = {}
-        for name, fl, by, a, b in prof:
-            d = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
-            d[0] += a.elapsed_time(b)
-            d[1] += fl
-            d[2] += by
-            d[3] += 1
-        total_ms = sum(d[0] for d in agg.values())
-        peak_tf, peak_gbs, peak_src = measured_peaks()
-        calls = {}
-        for name, (t_ms, fl, by, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-            calls[name] = {"ms": round(t_ms, 2), "launches": cnt, "tflops": round(fl / t_ms / 1e9, 1) if fl else None,
-                           "gbs": round(by / t_ms / 1e6, 1)}
-        # The dominant kernel is gemm_tcgen05_kernel: the plain GEMMs ("gemm") and the implicit-GEMM 3x3 convolutions
-        # ("conv3x3") are the same kernel template in its two addressing modes.
-        fam = {"gemm_tcgen05_kernel": ("gemm", "conv3x3"), "attn_spatial": ("attn_spatial",)}
-        fam_ms = {k: sum(agg[n][0] for n in names if n in agg) for k, names in fam.items()}
-        others = {n: agg[n][0] for n in agg if not any(n in names for names in fam.values())}
-        dname = max({**fam_ms, **others}.items(), key=lambda kv: kv[1])[0]
-        members = fam.get(dname, (dname,))
-        dms = sum(agg[n][0] for n in members if n in agg)
-        dfl = sum(agg[n][1] for n in members if n in agg)
-        dby = sum(agg[n][2] for n in members if n in agg)
-        dcnt = sum(agg[n][3] for n in members if n in agg)
-        tensor_bound = dname in ("gemm_tcgen05_kernel", "attn_spatial")
-        achieved = dfl / dms / 1e9 if tensor_bound else dby / dms / 1e6
-        peak = peak_tf if tensor_bound else peak_gbs
-        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of THIS gpu count, else null
-        traffic, traffic_src = None, None
-        tpath = ROOT / "profiles" / "ncu_traffic.json"
-        if tpath.exists():
-            ent = json.loads(tpath.read_text()).get(str(world), {}).get(dname)
-            if ent:
-                traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
-        roofline = {"kernel": dname, "bound": "tensor" if tensor_bound else "hbm", "achieved": round(achieved, 1),
-                    "peak": peak, "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": round(achieved / peak, 4),
-                    "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": round(dby / dcnt),
-                    "peak_source": peak_src, "launches": dcnt, "avg_launch_ms": round(dms / dcnt, 4),
-                    "share_of_bracketed_clip": round(dms / total_ms, 4),
-                    "whole_path_frac_of_tensor_peak": round(TFLOP_PER_FRAME * value / (world * peak_tf), 4)}
-
-        # ---- per-kernel table: CUPTI kernel records of one more clip executed exactly like the timed ones (graph replay) --
-        kernels, kernels_src = None, None
         try:
-            from torch.profiler import ProfilerActivity, profile
-            with profile(activities=[ProfilerActivity.CUDA]) as tp:
-                sync()  # CUPTI start-up differs per rank: this barrier absorbs the skew, not the clip's first collective
-                pipe.sample_tensors(dev_in, DDIM_STEPS, GUIDANCE)
-                torch.cuda.synchronize()
-            rows = {}
-            for ev in tp.key_averages():
-                us = getattr(ev, "device_time_total", None)
-                if us is None:
-                    us = getattr(ev, "cuda_time_total", 0.0)
-                if us <= 0:
-                    continue
-                if "AllReduce" in ev.key:
-                    continue  # the barrier above
-                nm = ev.key.replace("void ", "").split("(")[0]
-                nm = nm if len(nm) <= 72 else nm[:72]
-                r = rows.setdefault(nm, [0.0, 0])
-                r[0] += us / 1e3
-                r[1] += ev.count
-            tot = sum(v[0] for v in rows.values())
-            kernels = {k: {"ms": round(v[0], 2), "share": round(v[0] / tot, 4), "launches": v[1]}
-                       for k, v in sorted(rows.items(), key=lambda kv: -kv[1][0])[:24]}
-            kernels["_total_kernel_ms"] = round(tot, 1)
-            kernels_src = "CUPTI kernel records (torch.profiler) of one extra clip under CUDA-graph replay; not the timed clips"
-            fam_cupti = sum(v[0] for k, v in rows.items() if dname.split("_kernel")[0] in k)
-            roofline["cupti_ms_per_clip"] = round(fam_cupti, 1)
-            roofline["bracket_ms_per_clip"] = round(dms, 1)
-        except Exception as ex:  # noqa: BLE001 - the table is a diagnostic; the bench line must not depend on CUPTI
-            kernels_src = f"unavailable ({type(ex).__name__}: {ex})"
+            # ---- roofline of the dominant kernel: one extra, untimed clip with CUDA-event brackets around every C-ABI call ----
+            # The brackets must time kernels, not the host: each forward is preceded by a ~40 ms device-side spin so that the
+            # host runs ahead and the ~1 400 launches of the forward sit back to back in the stream when they execute.
+            # (Brackets are exact for long kernels - the GEMM / conv / attention families; they over-read the ~10 us kernels by
+            # launch latency, which is why the per-kernel table below comes from CUPTI on a graph-replay clip instead.)
+            den_eng = pipe.denoising_unet.engine()
+            orig_impl = den_eng._forward_impl
 
+            def queued_impl(*a):
+                torch.cuda._sleep(80_000_000)
+                return orig_impl(*a)
+
+            den_eng._forward_impl = queued_impl
+            ops.PROFILE = []
+            pipe.sample_tensors(dev_in, DDIM_STEPS, GUIDANCE)
+            torch.cuda.synchronize()
+            prof, ops.PROFILE = ops.PROFILE, None
+            den_eng._forward_impl = orig_impl
+            if args.dump_calls and rank == 0:
+                with open(args.dump_calls, "w") as fcsv:
+                    fcsv.write("idx,name,flops,bytes,ms\n")
+                    for i, (name, fl, by, a, b) in enumerate(prof):
+                        fcsv.write(f"{i},{name},{fl:.0f},{by:.0f},{a.elapsed_time(b):.4f}\n")
+            agg = {}
+            for name, fl, by, a, b in prof:
+                d = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+                d[0] += a.elapsed_time(b)
+                d[1] += fl
+                d[2] += by
+                d[3] += 1
+            total_ms = sum(d[0] for d in agg.values())
+            peak_tf, peak_gbs, peak_src = measured_peaks()
+            calls = {}
+            for name, (t_ms, fl, by, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+                calls[name] = {"ms": round(t_ms, 2), "launches": cnt, "tflops": round(fl / t_ms / 1e9, 1) if fl else None,
+                               "gbs": round(by / t_ms / 1e6, 1)}
+            # The dominant kernel is gemm_tcgen05_kernel: the plain GEMMs ("gemm") and the implicit-GEMM 3x3 convolutions
+            # ("conv3x3") are the same kernel template in its two addressing modes.
+            fam = {"gemm_tcgen05_kernel": ("gemm", "conv3x3"), "attn_spatial": ("attn_spatial",)}
+            fam_ms = {k: sum(agg[n][0] for n in names if n in agg) for k, names in fam.items()}
+            others = {n: agg[n][0] for n in agg if not any(n in names for names in fam.values())}
+            dname = max({**fam_ms, **others}.items(), key=lambda kv: kv[1])[0]
+            members = fam.get(dname, (dname,))
+            dms = sum(agg[n][0] for n in members if n in agg)
+            dfl = sum(agg[n][1] for n in members if n in agg)
+            dby = sum(agg[n][2] for n in members if n in agg)
+            dcnt = sum(agg[n][3] for n in members if n in agg)
+            tensor_bound = dname in ("gemm_tcgen05_kernel", "attn_spatial")
+            achieved = dfl / dms / 1e9 if tensor_bound else dby / dms / 1e6
+            peak = peak_tf if tensor_bound else peak_gbs
+            # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of THIS gpu count, else null
+            traffic, traffic_src = None, None
+            tpath = ROOT / "profiles" / "ncu_traffic.json"
+            if tpath.exists():
+                ent = json.loads(tpath.read_text()).get(str(world), {}).get(dname)
+                if ent:
+                    traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
+            roofline = {"kernel": dname, "bound": "tensor" if tensor_bound else "hbm", "achieved": round(achieved, 1),
+                        "peak": peak, "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": round(achieved / peak, 4),
+                        "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": round(dby / dcnt),
+                        "peak_source": peak_src, "launches": dcnt, "avg_launch_ms": round(dms / dcnt, 4),
+                        "share_of_bracketed_clip": round(dms / total_ms, 4),
+                        "whole_path_frac_of_tensor_peak": round(TFLOP_PER_FRAME * value / (world * peak_tf), 4)}
+
+            # ---- per-kernel table: CUPTI kernel records of one more clip executed exactly like the timed ones (graph replay) --
+            kernels, kernels_src = None, None
+            try:
+                from torch.profiler import ProfilerActivity, profile
+                with profile(activities=[ProfilerActivity.CUDA]) as tp:
+                    sync()  # CUPTI start-up differs per rank: this barrier absorbs the skew, not the clip's first collective
+                    pipe.sample_tensors(dev_in, DDIM_STEPS, GUIDANCE)
+                    torch.cuda.synchronize()
+                rows = {}
+                for ev in tp.key_averages():
+                    us = getattr(ev, "device_time_total", None)
+                    if us is None:
+                        us = getattr(ev, "cuda_time_total", 0.0)
+                    if us <= 0:
+                        continue
+                    if "AllReduce" in ev.key:
+                        continue  # the barrier above
+                    nm = ev.key.replace("void ", "").split("(")[0]
+                    nm = nm if len(nm) <= 72 else nm[:72]
+                    r = rows.setdefault(nm, [0.0, 0])
+                    r[0] += us / 1e3
+                    r[1] += ev.count
+                tot = sum(v[0] for v in rows.values())
+                kernels = {k: {"ms": round(v[0], 2), "share": round(v[0] / tot, 4), "launches": v[1]}
+                           for k, v in sorted(rows.items(), key=lambda kv: -kv[1][0])[:24]}
+                kernels["_total_kernel_ms"] = round(tot, 1)
+                kernels_src = "CUPTI kernel records (torch.profiler) of one extra clip under CUDA-graph replay; not the timed clips"
+                fam_cupti = sum(v[0] for k, v in rows.items() if dname.split("_kernel")[0] in k)
+                roofline["cupti_ms_per_clip"] = round(fam_cupti, 1)
+                roofline["bracket_ms_per_clip"] = round(dms, 1)
+            except Exception as ex:  # noqa: BLE001 - the table is a diagnostic; the bench line must not depend on CUPTI
+                kernels_src = f"unavailable ({type(ex).__name__}: {ex})"
+
+        except Exception as ex:  # noqa: BLE001 - the breakdown is diagnostic: the measured line above must still print
+            ops.PROFILE = None
+            eng = pipe.denoising_unet.engine()
+            eng.__dict__.pop("_forward_impl", None)  # drop the queued wrapper if it is still installed
+            roofline, kernels_src = None, f"breakdown failed ({type(ex).__name__}: {ex})"
     if rank != 0:
         return
-    cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline_sample(frames=8)
+    cpu = None
+    if not (args.no_cpu_baseline or world > 1):
+        try:
+            cpu = cpu_baseline_sample(frames=8)
+        except Exception as ex:  # noqa: BLE001 - a host-side failure must not cost the measured GPU line
+            cpu = {"value": None, "unit": "frames/s", "cores": usable_cores(), "kind": "port",
+                   "sample": f"failed: {type(ex).__name__}: {ex}"}
     par = "1 GPU"
     if world > 1:
         from mimo_b200.host.shard import ShardPlan
