@@ -325,6 +325,17 @@ class UNetEngine:
         wp, b = self.w[p]
         return ops.conv_up2x(x, wp, n, h, w, bias=b)  # Upsample3D (resnet.py:53-90) without the 4x tensor
 
+    def check_latent_size(self, h: int, w: int) -> None:
+        """The down path halves h and w once per level and the up path doubles them back exactly. The reference also
+        accepts sizes that do not divide (its script default 784 x 784 -> 98 x 98 latents) by interpolating every upsampler
+        to the skip connection's size (unet_3d_edit_bkfill.py:430-435, :544-545 `forward_upsample_size`); the fused
+        nearest-x2 + 3x3 kernel (mimo_conv_up2x) has no such mode: refuse instead of reading past the skip tensors."""
+        m = 1 << (len(self.spec.block_out_channels) - 1)
+        if h <= 0 or w <= 0 or h % m or w % m:
+            raise L.MimoError(f"latent size {h} x {w} is not a multiple of {m} (pixels: {8 * m}): the reference's "
+                              "forward_upsample_size path (unet_3d_edit_bkfill.py:430-435) is not implemented; "
+                              f"use a width and height that are multiples of {8 * m}")
+
     xchg = None  # host.shard.Exchange of this GPU's frame group (None / G == 1: all frames of a window are local)
     taps: Optional[dict] = None  # debugging aid (scripts/gpu_probe.py): block outputs as [N, C, H, W] fp32 on CPU
 
@@ -391,6 +402,7 @@ class UNetEngine:
         keys|values already projected with the READER's to_k/to_v: {path: [nb, hw, 2C]}. `self` is the reference
         UNet (motion=False). latents [nb, 4, h, w]."""
         nbr, c, h, w = latents.shape
+        self.check_latent_size(h, w)
         x_in = ops.ncfhw_to_nhwc(latents.to(self.device).unsqueeze(2).contiguous(), 8, self.dtype)
         tembs = self._time_embed(torch.zeros(nbr, device=self.device))
         st = {"xattn": self.cross_attn_vectors(ehs)}
@@ -484,6 +496,7 @@ class UNetEngine:
         st = self.clip_state
         assert st is not None, "begin_clip() must run before forward()"
         b, c, f, h, w = sample.shape
+        self.check_latent_size(h, w)
         if st["bank_index"] is None or st["bank_index"].numel() != b * f:
             self.begin_clip_frames(f, b)
         t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep])
@@ -535,6 +548,8 @@ class PoseGuiderEngine:
     def forward(self, cond: torch.Tensor) -> torch.Tensor:
         """cond [1, 3, F, H, W] -> channels-last [(F) H/8 W/8, 320]."""
         b, c, f, H, W = cond.shape
+        if H % 8 or W % 8:  # three stride-2 convolutions; the pipeline floors its images to multiples of 8 (:73-80)
+            raise L.MimoError(f"pose frames of {H} x {W}: height and width must be multiples of 8")
         x = ops.ncfhw_to_nhwc(cond.to(self.device).contiguous(), 8, self.dtype)
         n, h, w = b * f, H, W
         for name, stride in self.layers:
@@ -615,6 +630,10 @@ class VAEEncoderEngine(_VAEBlocks):
     def encode_mean(self, x: torch.Tensor) -> torch.Tensor:
         """x [n, 3, H, W] in [-1, 1] -> latent mean [n, 4, H/8, W/8] (not yet scaled by 0.18215)."""
         n, c, h, w = x.shape
+        m = 1 << sum(1 for i in range(self.n_down) if f"down{i}" in self.w)
+        if h % m or w % m:
+            raise L.MimoError(f"images of {h} x {w}: height and width must be multiples of {m} (VaeImageProcessor floors "
+                              "to multiples of the VAE scale factor, pipeline :73-80)")
         t = ops.ncfhw_to_nhwc(x.to(self.device).unsqueeze(2).contiguous(), 8, self.dtype)
         t = ops.conv3x3(t, self.w["conv_in"][0], n, h, w, bias=self.w["conv_in"][1])
         for i in range(self.n_down):

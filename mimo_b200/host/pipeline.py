@@ -279,6 +279,16 @@ class Pose2VideoPipeline:
             latents = latents.to(device)  # pipeline :179
         return latents * self.scheduler.init_noise_sigma
 
+    def check_size(self, width: int, height: int) -> None:
+        """Width and height must be multiples of 8 x 2^(UNet levels - 1) = 64 pixels. The reference also runs other sizes
+        (run_animate.py's default is 784 x 784) through `forward_upsample_size` (unet_3d_edit_bkfill.py:430-435), which
+        this engine does not implement: say so before any work is done."""
+        m = self.vae_scale_factor << (len(self.denoising_unet.config.block_out_channels) - 1)
+        if width % m or height % m:
+            raise NotImplementedError(f"width x height = {width} x {height}: both must be multiples of {m} (the "
+                                      "reference's forward_upsample_size path for other sizes is not implemented); "
+                                      f"e.g. {width // m * m or m} x {height // m * m or m}")
+
     # ------------------------------------------------------------------------------------------------
     def preprocess(self, ref_image, pose_images, vid_bk_images, width, height, video_length, generator,
                    dtype) -> Dict[str, torch.Tensor]:
@@ -511,6 +521,7 @@ class Pose2VideoPipeline:
             raise NotImplementedError("eta != 0, context_batch_size != 1, interpolation_factor >= 2 and "
                                       "num_images_per_prompt != 1 are outside the reference's shipped configuration")
         dtype = self.denoising_unet.dtype
+        self.check_size(width, height)
         host = self.preprocess(ref_image, pose_images, vid_bk_images, width, height, video_length, generator, dtype)
         dev_in = {k: v.to(device, non_blocking=True) for k, v in host.items()}
         self.io_bytes["h2d"] = sum(v.numel() * v.element_size() for v in host.values())

@@ -87,6 +87,32 @@ def test_unsupported_configurations_fail_loudly():
         ReferenceAttentionControl(m, mode="read", fusion_blocks="midup")
 
 
+def test_sizes_the_fused_upsampler_cannot_serve_are_refused():
+    """The reference runs any size through `forward_upsample_size` (unet_3d_edit_bkfill.py:430-435; run_animate.py's
+    default is 784 x 784 -> 98 x 98 latents); this engine's nearest-x2 + 3x3 kernel doubles exactly, so sizes that are
+    not multiples of 64 pixels (8 latent pixels) must fail before any work is done, not read past a skip tensor."""
+    from types import SimpleNamespace
+
+    from mimo_b200 import engine as E
+    from mimo_b200.host import pipeline as P
+    from mimo_b200.lib import MimoError
+    eng = SimpleNamespace(spec=E.UNetSpec())
+    for ok in ((64, 64), (96, 64), (8, 16)):
+        E.UNetEngine.check_latent_size(eng, *ok)
+    for bad in ((98, 98), (64, 100), (0, 64), (4, 8)):
+        with pytest.raises(MimoError, match="forward_upsample_size"):
+            E.UNetEngine.check_latent_size(eng, *bad)
+    E.UNetEngine.check_latent_size(SimpleNamespace(spec=E.UNetSpec(block_out_channels=(32, 64))), 6, 10)  # 2 levels: x2
+    pipe = P.Pose2VideoPipeline.__new__(P.Pose2VideoPipeline)
+    pipe.vae_scale_factor = 8
+    pipe.denoising_unet = SimpleNamespace(config=SimpleNamespace(block_out_channels=(320, 640, 1280, 1280)))
+    pipe.check_size(512, 512)
+    pipe.check_size(768, 512)
+    for bad in ((784, 784), (512, 520)):
+        with pytest.raises(NotImplementedError, match="multiples of 64"):
+            pipe.check_size(*bad)
+
+
 def test_image_preprocessing_is_the_vae_image_processor_bit_for_bit():
     """pipeline :73-80 / :424-453: the byte-level host path + device-side normalisation must reproduce
     VaeImageProcessor.preprocess (RGB, LANCZOS to multiples of 8, /255, NCHW, optional 2x-1) exactly."""
