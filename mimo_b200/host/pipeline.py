@@ -480,8 +480,11 @@ class Pose2VideoPipeline:
                                   frame_stride=h * w)
             else:
                 ops.cfg_ddim_step(noise_pred[0], noise_pred[0], latents, 1.0, *co, counter=counter, frame_stride=h * w)
-            if callback is not None and i % callback_steps == 0:
-                callback(i, t, latents)
+            # the reference's inner `for i in range(num_context_batches)` (pipeline :503-510) shadows the step index: its
+            # callback test (:556-561) and the index it passes see the LAST CONTEXT BATCH's index, at every step
+            i_ref = len(windows) - 1
+            if callback is not None and i_ref % callback_steps == 0:
+                callback(i_ref, t, latents)
         mark("denoise")
         reader.clear()
         writer.clear()

@@ -124,7 +124,8 @@ def _oracle_engines(monkeypatch, O, cfg, vcfg):
     monkeypatch.setattr(M.AutoencoderKL, "engine", cached(lambda sd: (Vae(sd), Vae(sd))))
 
 
-def test_reference_pipeline_file_runs_over_the_facades(compat_path, monkeypatch, golden_dir):
+@pytest.mark.parametrize("F_", [1, 26])
+def test_reference_pipeline_file_runs_over_the_facades(compat_path, monkeypatch, golden_dir, F_):
     import PIL.Image
     from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
 
@@ -138,9 +139,13 @@ def test_reference_pipeline_file_runs_over_the_facades(compat_path, monkeypatch,
     assert ref_mod.get_context_scheduler is context.get_context_scheduler
 
     g = torch.load(golden_dir / "pipeline_cfg1.pt")
-    seed, F_, size, steps = g["seed"], g["F"], g["size"], g["steps"]
+    seed, size, steps = g["seed"], g["size"], g["steps"]
+    assert g["F"] == 1
+    vae_widths = tuple(g["vae_widths"])
+    if F_ != 1:  # two context windows (24 + wrap-around): checked against oracle.sample_clip instead of the fixture
+        seed, size, vae_widths = 300, 64, (32, 64, 128, 128)
     widths = (128, 256, 512, 512)
-    cfg, vcfg = O.UNetConfig(block_out_channels=widths), O.VAEConfig(block_out_channels=tuple(g["vae_widths"]))
+    cfg, vcfg = O.UNetConfig(block_out_channels=widths), O.VAEConfig(block_out_channels=vae_widths)
     _oracle_engines(monkeypatch, O, cfg, vcfg)
     mk = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
               temporal_position_encoding=True, temporal_position_encoding_max_len=32, temporal_attention_dim_div=1)
@@ -150,11 +155,11 @@ def test_reference_pipeline_file_runs_over_the_facades(compat_path, monkeypatch,
                                  unet_use_temporal_attention=False)
     ref = M.UNet2DConditionModel(block_out_channels=widths, cross_attention_dim=768)
     pg = M.PoseGuider(widths[0], conditioning_channels=3, block_out_channels=(16, 32, 96, 256))
-    vae = M.AutoencoderKL(block_out_channels=tuple(g["vae_widths"]))
-    den.load_state_dict(O.make_denoising_unet_sd(cfg, seed), strict=True)
-    ref.load_state_dict(O.make_reference_unet_sd(cfg, seed + 1), strict=True)
-    pg.load_state_dict(O.make_pose_guider_sd(seed + 2, widths[0]), strict=True)
-    vae.load_state_dict(O.make_vae_sd(vcfg, seed + 3), strict=True)
+    vae = M.AutoencoderKL(block_out_channels=vae_widths)
+    sds = dict(den=O.make_denoising_unet_sd(cfg, seed), ref=O.make_reference_unet_sd(cfg, seed + 1),
+               pg=O.make_pose_guider_sd(seed + 2, widths[0]), vae=O.make_vae_sd(vcfg, seed + 3))
+    for m, k in ((den, "den"), (ref, "ref"), (pg, "pg"), (vae, "vae")):
+        m.load_state_dict(sds[k], strict=True)
     torch.manual_seed(seed + 4)
     clip = CLIPVisionModelWithProjection(CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2,
                                                           num_attention_heads=4, image_size=224, patch_size=32,
@@ -172,15 +177,35 @@ def test_reference_pipeline_file_runs_over_the_facades(compat_path, monkeypatch,
         a[size // 4: size // 2 + i % 8, size // 3: size // 3 + 40] = rng.randint(11, 256, 3)
         poses.append(PIL.Image.fromarray(a))
         bks.append(PIL.Image.fromarray(rng.randint(0, 256, (size, size, 3), dtype=np.uint8)))
+    seen = []
     with torch.no_grad():
-        out = pipe(ref_img, poses, bks, size, size, F_, steps, 3.5, generator=torch.manual_seed(42))
+        out = pipe(ref_img, poses, bks, size, size, F_, steps, 3.5, generator=torch.manual_seed(42),
+                   callback=lambda i, t, lat: seen.append((i, int(t))), callback_steps=1)
+    # the callback sees the inner loop's shadowed variable (:503-510): the index of the last context batch, at every step
+    assert seen == [(0 if F_ == 1 else 1, 999), (0 if F_ == 1 else 1, 499)]
     vid = out.videos
     assert vid.shape == (1, 3, F_, size, size) and vid.dtype == torch.float32
-    want = g["videos"].float()
-    got = vid[:, :, :, ::8, ::8]
-    err = float((got - want).norm() / want.norm())
-    assert err < 2e-3, err  # the fixture is stored in fp16
-    assert abs(float(vid.mean()) - g["videos_mean"]) < 1e-4
+    if F_ == 1:
+        want = g["videos"].float()
+        got = vid[:, :, :, ::8, ::8]
+        err = float((got - want).norm() / want.norm())
+        assert err < 2e-3, err  # the fixture is stored in fp16
+        assert abs(float(vid.mean()) - g["videos_mean"]) < 1e-4
+    else:
+        from mimo_b200.host.pipeline import pil_to_tensor
+        never = []
+        with torch.no_grad():
+            pipe(ref_img, poses, bks, size, size, F_, 1, 3.5, generator=torch.manual_seed(42),
+                 callback=lambda *a: never.append(a), callback_steps=2)
+            assert never == []  # 1 % 2 != 0: with two windows and callback_steps = 2 the reference never calls back
+            emb = clip(pipe.clip_image_processor.preprocess(ref_img.resize((224, 224)), return_tensors="pt").pixel_values).image_embeds
+            lat0 = torch.randn((1, 4, F_, size // 8, size // 8), generator=torch.manual_seed(42), dtype=torch.float32)
+            W = O.Weights(sds["den"], sds["ref"], sds["pg"], sds["vae"], cfg, vcfg)
+            ref_out = O.sample_clip(W, pil_to_tensor(ref_img, size, size, True),
+                                    pil_to_tensor(poses, size, size, False).permute(1, 0, 2, 3).unsqueeze(0),
+                                    pil_to_tensor(bks, size, size, True), emb, lat0, steps, 3.5)
+        err = float((vid - ref_out["videos"]).norm() / ref_out["videos"].norm())
+        assert err < 1e-4, err  # fp32 both sides
     assert den._engine.clip_state is None  # reference_control_reader.clear() reached the engine
 
 

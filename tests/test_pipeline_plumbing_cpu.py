@@ -91,7 +91,14 @@ def test_own_sampler_host_logic_on_cpu(monkeypatch, golden_dir, F_):
         bks.append(PIL.Image.fromarray(rng.randint(0, 256, (size, size, 3), dtype=np.uint8)))
     with torch.no_grad():
         host = pipe.preprocess(ref_img, poses, bks, size, size, F_, torch.manual_seed(42), torch.float32)
-        out = pipe.sample_tensors(host, steps, 3.5)
+        seen, never = [], []
+        out = pipe.sample_tensors(host, steps, 3.5, callback=lambda i, t, lat: seen.append((i, int(t), tuple(lat.shape))))
+        pipe.sample_tensors(host, 1, 3.5, callback=lambda *a: never.append(a), callback_steps=2, decode=False)
+    # the reference's callback sees the shadowed loop variable (pipeline :503-510, :556-561): the index of the last context
+    # batch at every step - pinned on the reference's own file in tests/test_dropin_cpu.py
+    nwin = 1 if F_ == 1 else 2
+    assert seen == [(nwin - 1, t, (1, 4, F_, size // 8, size // 8)) for t in (999, 499)]
+    assert len(never) == (1 if nwin == 1 else 0)  # (nwin - 1) % 2: 0 -> called, 1 -> never
     vid = out["videos"]
     assert vid.shape == (1, 3, F_, size, size)
     if F_ == 1:
