@@ -264,7 +264,6 @@ class UNet3DConditionModel(_UNetBase):
         self._init_unet(block_out_channels, layers_per_block, cross_attention_dim, attention_head_dim, norm_num_groups,
                         norm_eps, 8, out_channels,  # in_channels is forced to 8 (unet_3d_edit_bkfill.py:88)
                         dict(sample_size=sample_size), motion_max_len=self._motion_max_len)
-        self._xattn_key = None
 
     @classmethod
     def from_pretrained_2d(cls, pretrained_model_path, motion_module_path, subfolder=None,
@@ -307,10 +306,9 @@ class UNet3DConditionModel(_UNetBase):
         if eng.clip_state is None:
             raise MimoError("denoising_unet.forward before ReferenceAttentionControl.update(): no reference banks")
         b, c, f, h, w = sample.shape
-        key = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, tuple(encoder_hidden_states.shape))
-        if key != self._xattn_key:
-            eng.set_cross_attn(encoder_hidden_states)
-            self._xattn_key = key
+        # re-folded on every call (32 one-row GEMMs, ~0.4 % of a forward): neither data_ptr nor torch's version counter
+        # identify the CONTENT of a tensor whose storage the caching allocator recycles, and a stale vector is silent
+        eng.set_cross_attn(encoder_hidden_states)
         pose = None
         if pose_cond_fea is not None:
             from .. import ops
@@ -353,7 +351,6 @@ class ReferenceAttentionControl:
         else:
             banks = ref.write_banks(latents, ehs, den)
         den.begin_clip(ehs, banks, cfg=self.cfg, frames=1, branches=getattr(self.unet, "_branches", None))
-        self.unet._xattn_key = None
 
     def clear(self):
         eng = self.unet._engine

@@ -223,6 +223,17 @@ class Pose2VideoPipeline:
     def device(self) -> torch.device:
         return self.denoising_unet.device
 
+    @property
+    def _execution_device(self) -> torch.device:  # pipeline :98-112 (no accelerate hooks here: the models' device)
+        return self.device
+
+    def enable_vae_slicing(self):
+        """pipeline :82-86. diffusers' slicing bounds the decoder's activation memory by decoding one image at a time; the
+        engine decodes a clip's frames in one batched pass (per GPU: < 3 GB at 512 x 512 x 24 frames): nothing to switch."""
+
+    def disable_vae_slicing(self):
+        """See enable_vae_slicing()."""
+
     def _clip_pixels(self, ref_image: PIL.Image.Image) -> torch.Tensor:
         if self._clip_image_processor is None:
             from transformers import CLIPImageProcessor
