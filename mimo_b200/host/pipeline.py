@@ -490,7 +490,9 @@ class Pose2VideoPipeline:
                 ops.cfg_ddim_step(noise_pred[0], noise_pred[1], latents, guidance_scale, *co, counter=counter,
                                   frame_stride=h * w)
             else:
-                ops.cfg_ddim_step(noise_pred[0], noise_pred[0], latents, 1.0, *co, counter=counter, frame_stride=h * w)
+                # the reference divides the window sums by `counter` only inside its guidance branch (pipeline :545-549):
+                # without CFG, frames that two windows cover keep the SUM of both predictions - mirrored, not repaired
+                ops.cfg_ddim_step(noise_pred[0], noise_pred[0], latents, 1.0, *co, counter=None, frame_stride=h * w)
             # the reference's inner `for i in range(num_context_batches)` (pipeline :503-510) shadows the step index: its
             # callback test (:556-561) and the index it passes see the LAST CONTEXT BATCH's index, at every step
             i_ref = len(windows) - 1

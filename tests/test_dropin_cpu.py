@@ -124,8 +124,8 @@ def _oracle_engines(monkeypatch, O, cfg, vcfg):
     monkeypatch.setattr(M.AutoencoderKL, "engine", cached(lambda sd: (Vae(sd), Vae(sd))))
 
 
-@pytest.mark.parametrize("F_", [1, 26])
-def test_reference_pipeline_file_runs_over_the_facades(compat_path, monkeypatch, golden_dir, F_):
+@pytest.mark.parametrize("F_,guidance", [(1, 3.5), (26, 3.5), (26, 1.0)])
+def test_reference_pipeline_file_runs_over_the_facades(compat_path, monkeypatch, golden_dir, F_, guidance):
     import PIL.Image
     from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
 
@@ -179,7 +179,7 @@ def test_reference_pipeline_file_runs_over_the_facades(compat_path, monkeypatch,
         bks.append(PIL.Image.fromarray(rng.randint(0, 256, (size, size, 3), dtype=np.uint8)))
     seen = []
     with torch.no_grad():
-        out = pipe(ref_img, poses, bks, size, size, F_, steps, 3.5, generator=torch.manual_seed(42),
+        out = pipe(ref_img, poses, bks, size, size, F_, steps, guidance, generator=torch.manual_seed(42),
                    callback=lambda i, t, lat: seen.append((i, int(t))), callback_steps=1)
     # the callback sees the inner loop's shadowed variable (:503-510): the index of the last context batch, at every step
     assert seen == [(0 if F_ == 1 else 1, 999), (0 if F_ == 1 else 1, 499)]
@@ -195,7 +195,7 @@ def test_reference_pipeline_file_runs_over_the_facades(compat_path, monkeypatch,
         from mimo_b200.host.pipeline import pil_to_tensor
         never = []
         with torch.no_grad():
-            pipe(ref_img, poses, bks, size, size, F_, 1, 3.5, generator=torch.manual_seed(42),
+            pipe(ref_img, poses, bks, size, size, F_, 1, guidance, generator=torch.manual_seed(42),
                  callback=lambda *a: never.append(a), callback_steps=2)
             assert never == []  # 1 % 2 != 0: with two windows and callback_steps = 2 the reference never calls back
             emb = clip(pipe.clip_image_processor.preprocess(ref_img.resize((224, 224)), return_tensors="pt").pixel_values).image_embeds
@@ -203,7 +203,7 @@ def test_reference_pipeline_file_runs_over_the_facades(compat_path, monkeypatch,
             W = O.Weights(sds["den"], sds["ref"], sds["pg"], sds["vae"], cfg, vcfg)
             ref_out = O.sample_clip(W, pil_to_tensor(ref_img, size, size, True),
                                     pil_to_tensor(poses, size, size, False).permute(1, 0, 2, 3).unsqueeze(0),
-                                    pil_to_tensor(bks, size, size, True), emb, lat0, steps, 3.5)
+                                    pil_to_tensor(bks, size, size, True), emb, lat0, steps, guidance)
         err = float((vid - ref_out["videos"]).norm() / ref_out["videos"].norm())
         assert err < 1e-4, err  # fp32 both sides
     assert den._engine.clip_state is None  # reference_control_reader.clear() reached the engine

@@ -23,8 +23,8 @@ class _Event:
         return 0.0
 
 
-@pytest.mark.parametrize("F_", [1, 26])
-def test_own_sampler_host_logic_on_cpu(monkeypatch, golden_dir, F_):
+@pytest.mark.parametrize("F_,guidance", [(1, 3.5), (26, 3.5), (26, 1.0)])
+def test_own_sampler_host_logic_on_cpu(monkeypatch, golden_dir, F_, guidance):
     import PIL.Image
     from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
 
@@ -92,8 +92,8 @@ def test_own_sampler_host_logic_on_cpu(monkeypatch, golden_dir, F_):
     with torch.no_grad():
         host = pipe.preprocess(ref_img, poses, bks, size, size, F_, torch.manual_seed(42), torch.float32)
         seen, never = [], []
-        out = pipe.sample_tensors(host, steps, 3.5, callback=lambda i, t, lat: seen.append((i, int(t), tuple(lat.shape))))
-        pipe.sample_tensors(host, 1, 3.5, callback=lambda *a: never.append(a), callback_steps=2, decode=False)
+        out = pipe.sample_tensors(host, steps, guidance, callback=lambda i, t, lat: seen.append((i, int(t), tuple(lat.shape))))
+        pipe.sample_tensors(host, 1, guidance, callback=lambda *a: never.append(a), callback_steps=2, decode=False)
     # the reference's callback sees the shadowed loop variable (pipeline :503-510, :556-561): the index of the last context
     # batch at every step - pinned on the reference's own file in tests/test_dropin_cpu.py
     nwin = 1 if F_ == 1 else 2
@@ -113,7 +113,7 @@ def test_own_sampler_host_logic_on_cpu(monkeypatch, golden_dir, F_):
             W = O.Weights(sds["den"], sds["ref"], sds["pg"], sds["vae"], cfg, vcfg)
             ref_out = O.sample_clip(W, pil_to_tensor(ref_img, size, size, True),
                                     pil_to_tensor(poses, size, size, False).permute(1, 0, 2, 3).unsqueeze(0),
-                                    pil_to_tensor(bks, size, size, True), emb, lat0, steps, 3.5)
+                                    pil_to_tensor(bks, size, size, True), emb, lat0, steps, guidance)
         err = float((out["latents"] - ref_out["latents"]).norm() / ref_out["latents"].norm())
         assert err < 1e-4, err  # fp32 both sides: only summation-order noise
         assert float((vid.float() - ref_out["videos"]).norm() / ref_out["videos"].norm()) < 1e-4
