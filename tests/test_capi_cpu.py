@@ -59,3 +59,29 @@ def test_geglu_granule_and_arg_validation():
     p = L.GemmParams()
     assert lib.mimo_gemm(ctypes.byref(p), None) == -1  # MIMO_ERR_ARG: null pointers
     assert b"null" in lib.mimo_last_error()
+
+
+def test_integration_md_stub_binds_the_library():
+    """The ctypes stub INTEGRATION.md shows a maintainer (section 2) is executed as written up to its first GPU call: the
+    struct mirror must match the C struct, the workspace query must answer on the CPU, and a launch without a device
+    must come back as an error string, not a crash."""
+    import os
+    text = (ROOT / "INTEGRATION.md").read_text()
+    block = re.search(r"```python\n(# src/models/resnet\.py.*?)```", text, flags=re.S).group(1)
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)  # the stub loads "mimo_b200/libmimo_b200.so" relative to the checkout
+    try:
+        exec(compile(block, "INTEGRATION.md:stub", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    lib, P = ns["_lib"], ns["GroupNormParams"]
+    p = P(1 << 20, 320, None, 0, 1 << 20, 1 << 20, 1 << 20, None, 2, 4096, 32, 1e-5, 1, 0)
+    need = lib.mimo_groupnorm_workspace_bytes(ctypes.byref(p))
+    assert need > 0 and need % 8 == 0
+    bad = P(1 << 20, 321, None, 0, 1 << 20, 1 << 20, 1 << 20, None, 2, 4096, 32, 1e-5, 1, 0)
+    assert lib.mimo_groupnorm_workspace_bytes(ctypes.byref(bad)) < 0 and b"multiples of 8" in lib.mimo_last_error()
+    if not torch.cuda.is_available():
+        p.stats = 1 << 20
+        assert lib.mimo_groupnorm(ctypes.byref(p), None) < 0
+        assert b"CUDA" in lib.mimo_last_error() or b"fallback" in lib.mimo_last_error()
