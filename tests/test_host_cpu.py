@@ -319,3 +319,18 @@ def test_context_windows_sweep_against_the_reference_generated_fixture(golden_di
         assert context.get_total_steps(sched, list(range(n)), 20, frames, size, stride, overlap) == want
     import src.pipelines.context as overlay  # the reference's import path resolves to the same functions
     assert overlay.get_total_steps is context.get_total_steps and overlay.uniform is context.uniform
+
+
+def test_parameter_counts_equal_the_published_checkpoints():
+    """The third-party architectures are restated (diffusers is not installable here), so their LAYER SHAPES are pinned
+    against public facts: Stable Diffusion 1.5's UNet2DConditionModel has 859 520 964 parameters and sd-vae-ft-mse's
+    AutoencoderKL 83 653 863 (encoder 34 163 592, decoder 49 490 179, quant + post-quant convs 92) - the schema the
+    facades materialise and the oracle's generator must give exactly those numbers."""
+    import math
+    n = lambda s: sum(math.prod(v) for v in s.values())
+    assert n(schema.unet_schema(in_channels=4, motion=False, out_head=True)) == 859_520_964
+    v = schema.vae_schema()
+    assert n(v) == 83_653_863
+    assert n({k: s for k, s in v.items() if k.startswith("encoder.")}) == 34_163_592
+    assert n({k: s for k, s in v.items() if k.startswith("decoder.")}) == 49_490_179
+    assert sum(t.numel() for t in O.make_vae_sd(O.VAEConfig(), 0).values()) == 83_653_863
