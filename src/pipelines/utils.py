@@ -16,12 +16,12 @@ def set_tensor_interpolation_method(is_slerp):
 
 
 def linear(v1, v2, t):
-    return v1 + t * (v2 - v1)
+    return (1.0 - t) * v1 + t * v2  # this evaluation order: bit-identical to the reference's
 
 
 def slerp(v0: torch.Tensor, v1: torch.Tensor, t: float, DOT_THRESHOLD: float = 0.9995) -> torch.Tensor:
     cos = (v0 / v0.norm() * (v1 / v1.norm())).sum()
     if cos.abs() > DOT_THRESHOLD:  # nearly parallel: the great-circle formula is ill-conditioned
-        return linear(v0, v1, t)
+        return (1.0 - t) * v0 + t * v1
     theta = cos.acos()
     return (torch.sin((1.0 - t) * theta) * v0 + torch.sin(t * theta) * v1) / torch.sin(theta)

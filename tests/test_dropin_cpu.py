@@ -361,3 +361,22 @@ def test_scene_compositing_matches_the_reference_loop(compat_path, monkeypatch):
     got = composite.composite_clip(video, contexts, bboxes, bk, vid, None, pads, padvs, mask_list, n_frames, overlay, device="cpu")
     for i in range(n_frames):
         assert np.array_equal(ns["res_images"][i], got[i]), i
+
+
+def test_overlay_pipeline_utils_equal_the_reference():
+    """src/pipelines/utils.py (imported by the reference's pipeline file, dead at interpolation_factor = 1): the overlay's
+    registry, linear and slerp against the reference's own file, bit for bit."""
+    spec = importlib.util.spec_from_file_location("_ref_pipeline_utils", REF / "src" / "pipelines" / "utils.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    import src.pipelines.utils as ours
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.randn(4, 8, 8, generator=g), torch.randn(4, 8, 8, generator=g)
+    for t in (0.0, 0.25, 0.5, 0.9):
+        assert torch.equal(ours.linear(a, b, t), ref.linear(a, b, t))
+        assert torch.equal(ours.slerp(a, b, t), ref.slerp(a, b, t))
+        assert torch.equal(ours.slerp(a, a * 1.0001, t), ref.slerp(a, a * 1.0001, t))  # nearly parallel: the linear branch
+    for flag in (True, False):
+        ours.set_tensor_interpolation_method(flag)
+        ref.set_tensor_interpolation_method(flag)
+        assert ours.get_tensor_interpolation_method().__name__ == ref.get_tensor_interpolation_method().__name__
